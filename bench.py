@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the per-record hash path (BASELINE.json configs[1], "C2"):
+10 M synthetic 250-bp amplicon reads, SHA-1 (value) and XXH3 (extra object), per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One process per GPU (torchrun for N > 1, weak scaling: every rank hashes its own 10 M records; no
+data-path collective — records are independent).  A step = one pass of the hot path
+(upper-case -> hash) over the rank's whole batch.  `value` is kernel-only (inputs resident in HBM, CUDA
+events on the launching stream, max over ranks); `e2e` goes through the C ABI with HOST buffers
+(pinned H2D, kernels, D2H inside the timed region).  `--impl reference` times the CPU restatement of the
+reference (the oracle; the Go reference cannot be built in this image) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RECORDS = 10_000_000
+READ_LEN = 250
+SEED = 0xC2
+LOWER_PERMILLE = 50            # 5 % soft-masked bases so upper-casing has work to do
+SHA1_INSTR_PER_BLOCK = 613     # SURVEY.md §8d contract figure (LOP3/IADD3/SHF/PRMT fused-op count)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [x.strip() for x in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of seqhasher.go:241-259 on all host cores, same workload shape."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+
+    from oracle import oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from synth import synth_bytes
+    cores = os.cpu_count() or 1
+    accel = O.lib().sho_accel_available()
+    base_n = 200_000
+    tile = 10                                   # 2 M records = 500 MB per step
+    res = np.tile(synth_bytes(base_n * READ_LEN, SEED, LOWER_PERMILLE), tile)
+    n = base_n * tile
+    offs = np.arange(n + 1, dtype=np.int64) * READ_LEN
+    for _ in range(max(args.warmup, 1)):
+        O.batch(res[: 50_000 * READ_LEN], offs[:50_001], ["sha1"], 1, threads=cores, accel=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.batch(res, offs, ["sha1"], 1, threads=cores, accel=True)
+    dt = (time.perf_counter() - t0) / args.steps
+    t1 = time.perf_counter()
+    O.batch(res[: 400_000 * READ_LEN], offs[:400_001], ["sha1"], 1, threads=1, accel=True)
+    dt1 = time.perf_counter() - t1
+    val = n / dt
+    sample = (f"{n} x {READ_LEN} bp reads per step (2 M-record sample of the 10 M workload, 200 k-read block tiled x10), "
+              f"sha1 + upper-casing, OpenMP record sharding over {cores} threads, "
+              f"{'OpenSSL SHA1 (SHA-NI)' if accel & 1 else 'portable C SHA-1'}")
+    line = {"impl": "reference", "metric": "sha1 seqs/s hashed, 250-bp reads", "value": val, "unit": "seqs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "gbps": val * READ_LEN / 1e9,
+            "config": {"workload": "C2: 250-bp amplicon reads, sha1, upper-casing on (bounded 2 M-record sample per step)"},
+            "cpu_baseline": {"value": val, "unit": "seqs/s", "cores": cores, "kind": "port", "sample": sample,
+                             "single_thread_value": 400_000 / dt1},
+            "e2e": {"value": val, "unit": "seqs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--records", type=int, default=N_RECORDS, help="records per GPU (default: the C2 size)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    from seqhasher_b200 import binding as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    B.init(0)
+    dev = torch.device("cuda", local)
+    st = torch.cuda.current_stream().cuda_stream
+    hbm_peak, peak_src = load_peaks()
+
+    n, L = args.records, READ_LEN
+    total = n * L
+    d_res = torch.empty(total + 16, dtype=torch.uint8, device=dev)
+    B.synth_fill(d_res.data_ptr(), total, SEED + rank, LOWER_PERMILLE, 0, stream=st, device=local)
+    d_offs = torch.arange(0, n + 1, dtype=torch.int64, device=dev) * L
+    flags = B.FLAG_UPPER
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_kernel(algo: str):
+        out = torch.empty(n * B.DIGEST_SIZES[B.algo_id(algo)], dtype=torch.uint8, device=dev)
+        run = lambda: B.hash_device(d_res.data_ptr(), d_offs.data_ptr(), n, total, [algo], flags, [out.data_ptr()],
+                                    stream=st, device=local)
+        for _ in range(args.warmup):
+            run()
+        barrier()
+        l0 = B.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as cs:
+            e0.record()
+            for _ in range(args.steps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+        launches = B.launch_count() - l0
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        return ms, launches, cs.summary(), out
+
+    ms_sha1, launches, clocks, out_sha1 = time_kernel("sha1")
+    ms_xxh3, _, clocks_x, _ = time_kernel("xxh3")
+
+    # ---- roofline of the two kernels (one launch per step each) ----
+    blocks_per_rec = (L + 9 + 63) // 64
+    int_peak, int_src = None, "theoretical issue peak 148 SM x 128 lanes x 1.965 GHz"
+    try:
+        int_peak = B.probe_int_peak(7, 2000, device=local)   # SHA-1 compression on register data, measured live
+        int_src = "measured live: SHA-1 compress loop on register data (shb_probe_int_peak kind 7)"
+    except Exception:
+        pass
+    theo = 148 * 128 * 1.965e9
+    sha1_ach = n * blocks_per_rec * SHA1_INSTR_PER_BLOCK / (ms_sha1 * 1e-3)
+    alg_bytes_sha1 = total + 8 * (n + 1) + 20 * n
+    alg_bytes_xxh3 = total + 8 * (n + 1) + 8 * n
+    roof_sha1 = {"bound": "int", "achieved": sha1_ach / 1e12, "peak": (int_peak or theo) / 1e12, "unit": "T lane-instr/s",
+                 "frac": sha1_ach / (int_peak or theo), "peak_source": int_src, "frac_of_theoretical_issue": sha1_ach / theo,
+                 "work": f"{SHA1_INSTR_PER_BLOCK} int ops x {blocks_per_rec} blocks x {n} records per launch",
+                 "hbm_gbps": alg_bytes_sha1 / (ms_sha1 * 1e-3) / 1e9, "traffic": None, "kernel": "hash_direct_kernel<sha1>"}
+    xxh3_gbps = alg_bytes_xxh3 / (ms_xxh3 * 1e-3) / 1e9
+    roof_xxh3 = {"bound": "hbm", "achieved": xxh3_gbps, "peak": hbm_peak, "unit": "GB/s", "frac": xxh3_gbps / hbm_peak,
+                 "peak_source": peak_src, "traffic": None, "kernel": "hash_direct_kernel<xxh3>",
+                 "bytes": f"{alg_bytes_xxh3} algorithmic bytes per launch (residues + 8 B offsets + 8 B digest per record)"}
+
+    # ---- e2e through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        parts = 8
+        per = (n + parts - 1) // parts
+        batches = []
+        for p in range(parts):
+            lo, hi = p * per, min(n, (p + 1) * per)
+            if hi <= lo:
+                break
+            b = B.Batch((hi - lo) * L, hi - lo, device=local)
+            torch.from_numpy(b.residues)[: (hi - lo) * L].copy_(d_res[lo * L: hi * L])
+            b.offsets[: hi - lo + 1] = np.arange(hi - lo + 1, dtype=np.int64) * L
+            b.n = hi - lo
+            batches.append(b)
+        torch.cuda.synchronize()
+
+        def step():
+            for b in batches:
+                b.submit(["sha1"], flags)
+            for b in batches:
+                b.wait()
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+        barrier()
+        dt = max_over_ranks(dt) / args.steps
+        # parity of the two paths on this rank
+        got = np.concatenate([b.digests(0) for b in batches])
+        same = bool((torch.from_numpy(got).reshape(-1) == out_sha1.cpu()).all())
+        e2e = {"value": n * world / dt, "unit": "seqs/s", "h2d_bytes_per_step": (total + 8 * (n + parts)) * world,
+               "d2h_bytes_per_step": 20 * n * world, "ms_per_step": dt * 1e3, "gbps": n * world * L / dt / 1e9,
+               "api": f"shb_submit/shb_wait on {len(batches)} pinned batches in flight per GPU", "matches_device_path": same}
+        for b in batches:
+            b.close()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        sample_n = min(n, 2_000_000)
+        h_res = d_res[: sample_n * L].cpu().numpy()
+        h_offs = np.arange(sample_n + 1, dtype=np.int64) * L
+        O.batch(h_res[: 20_000 * L], h_offs[:20_001], ["sha1"], flags, threads=cores, accel=True)
+        t0 = time.perf_counter()
+        want, _ = O.batch(h_res, h_offs, ["sha1"], flags, threads=cores, accel=True)
+        dt = time.perf_counter() - t0
+        ok = bool((torch.from_numpy(want[0]).reshape(-1) == out_sha1[: sample_n * 20].cpu()).all())
+        accel = O.lib().sho_accel_available()
+        cpu = {"value": sample_n / dt, "unit": "seqs/s", "cores": cores, "kind": "port",
+               "sample": f"first {sample_n} of the {n} records, sha1 + upper-casing, OpenMP over {cores} threads, "
+                         f"{'OpenSSL SHA1' if accel & 1 else 'portable C SHA-1'}; GPU digests equal: {ok}"}
+
+    if rank == 0:
+        val = n * world / (ms_sha1 * 1e-3)
+        line = {"metric": "sha1 seqs/s hashed, 250-bp reads", "value": val, "unit": "seqs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_sha1, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "gbps": val * L / 1e9,
+                "config": {"workload": f"C2: {n} x {L} bp synthetic amplicon reads per GPU, sha1, upper-casing on",
+                           "flags": "upper", "l2": f"inputs {total / 1e9:.2f} GB per step > 126 MB L2 (no reuse across steps)",
+                           "parallelism": f"record-range sharding x{world}, no collective"},
+                "roofline": roof_sha1,
+                "xxh3": {"value": n * world / (ms_xxh3 * 1e-3), "unit": "seqs/s", "ms_per_step": ms_xxh3,
+                         "gbps": n * world * L / (ms_xxh3 * 1e-3) / 1e9, "roofline": roof_xxh3, "clocks": clocks_x},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+/*
+ * seqhash_b200.h — C ABI of libseqhash_b200.so, the B200 (sm_100a) batch hashing engine that
+ * replaces the per-record hash path of vmikk/seqhasher.
+ *
+ * What it replaces.  The reference has no FFI/plugin seam; its hot path is the body of the
+ * per-record loop in processSequences:
+ *     seqhasher.go:246      seq = bytes.Join(bytes.Fields(seq), nil)     (whitespace strip)
+ *     seqhasher.go:249-251  seq = bytes.ToUpper(seq) unless --casesensitive
+ *     seqhasher.go:255-259  for each hash type: getHashFunc(t)(seq)
+ *     seqhasher.go:290-349  getHashFunc: 12 algorithms, empty-sequence rule, output format
+ * A per-record C call is useless for a GPU, so this ABI lifts exactly those statements to
+ * BATCH granularity: the host packs records into a CSR batch (one concatenated residue
+ * buffer + int64 offsets), submits it, and receives raw digests in input order.  Each entry
+ * point below names the reference statement it stands in for.  INTEGRATION.md shows the cgo
+ * shim a seqhasher maintainer would add.
+ *
+ * Conventions: plain C types only; the library owns every buffer it hands out; return codes
+ * (0 ok, <0 error, text via shb_last_error()); nothing is written to stderr/stdout; there is
+ * NO CPU fallback — every call fails with SHB_ERR_NO_DEVICE when no sm_100 GPU is usable.
+ * Raw digests are laid out so that lowercase hex of the bytes equals the reference string:
+ * byte digests verbatim; word hashes big-endian (fmt "%016x"/"%08x"); cityhash High||Low
+ * (seqhasher.go:316); murmur3 h1||h2 (seqhasher.go:319).
+ */
+#ifndef SEQHASH_B200_H
+#define SEQHASH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Algorithm ids = index into supportedHashTypes (seqhasher.go:41). */
+enum shb_algo {
+    SHB_SHA1 = 0, SHB_SHA3 = 1, SHB_MD5 = 2, SHB_XXHASH = 3, SHB_XXH3 = 4, SHB_CITYHASH = 5,
+    SHB_MURMUR3 = 6, SHB_NTHASH = 7, SHB_BLAKE3 = 8, SHB_K12 = 9, SHB_RAPIDHASH = 10,
+    SHB_RAPIDHASH32 = 11, SHB_N_ALGOS = 12
+};
+
+/* Normalisation flags of shb_submit / shb_hash_device. */
+#define SHB_FLAG_UPPER 1u     /* ASCII a-z -> A-Z: seqhasher.go:249-251 (set unless --casesensitive) */
+#define SHB_FLAG_STRIP 2u     /* drop \t \n \v \f \r ' ': seqhasher.go:246 */
+#define SHB_FLAG_EMIT_SEQ 4u  /* also return the normalised sequences (record.Seq.Seq = seq, :252) */
+
+/* Error codes. */
+#define SHB_OK 0
+#define SHB_ERR_NO_DEVICE (-1)   /* no CUDA device / not sm_100 / CUDA runtime failure at init */
+#define SHB_ERR_BAD_ARG (-2)
+#define SHB_ERR_CAPACITY (-3)    /* batch larger than the capacity given to shb_batch_create */
+#define SHB_ERR_CUDA (-4)        /* a CUDA call failed; see shb_last_error() */
+#define SHB_ERR_OFFSETS (-5)     /* offsets not monotone / record longer than 2^32-1 bytes */
+
+/* Library lifetime.  n_gpus <= 0 uses every visible device; devices 0..n-1 otherwise.  Returns the
+ * number of devices in use (>0) or an error.  Idempotent. */
+int shb_init(int n_gpus, int flags);
+void shb_shutdown(void);
+const char *shb_last_error(void);   /* thread-local text of the last failure */
+const char *shb_version(void);
+
+/* Name <-> id.  shb_algo_id is isValidHashType + lookup (seqhasher.go:142-149): exact match only,
+ * -1 otherwise.  NOTE the reference hashes any name it does not recognise inside getHashFunc
+ * (e.g. the untrimmed " md5" that passes validation) as SHA-1 (seqhasher.go:344-346); the host
+ * maps such names to SHB_SHA1 before calling — see seqhasher_b200/host. */
+int shb_algo_id(const char *name);
+const char *shb_algo_name(int algo);
+size_t shb_digest_size(int algo);   /* 20,64,16,8,8,16,16,8,32,128,8,4 bytes */
+
+/* ---- host-buffer path: one shb_batch = pinned staging + device buffers + a CUDA stream ---- */
+
+typedef struct shb_batch shb_batch;
+
+/* Capacity in residue bytes and records.  Two or more batches in flight give the double
+ * buffering (H2D of batch k+1 overlaps the kernels of batch k).  shb_batch_create uses device 0;
+ * shb_batch_create_on binds the batch to one of the devices selected by shb_init. */
+shb_batch *shb_batch_create(size_t max_bytes, size_t max_records);
+shb_batch *shb_batch_create_on(int device, size_t max_bytes, size_t max_records);
+void shb_batch_destroy(shb_batch *b);
+
+/* Pinned host staging the caller fills: record i is residues[offsets[i] .. offsets[i+1]),
+ * offsets[0] == 0, n+1 monotone entries (the CSR form of `record.Seq.Seq`, seqhasher.go:241). */
+uint8_t *shb_batch_residues(shb_batch *b);
+int64_t *shb_batch_offsets(shb_batch *b);
+
+/* Asynchronous: H2D copy, [strip], [upper], one digest set per algo, D2H copy, all on the batch's
+ * stream.  Replaces seqhasher.go:246-259 for n_records records at once.  algos may repeat (the
+ * reference allows "--hash sha1,sha1"); slot k of the outputs belongs to algos[k]. */
+int shb_submit(shb_batch *b, size_t n_records, const int *algos, int n_algos, unsigned flags);
+/* Blocks until the batch's outputs are valid in host memory. */
+int shb_wait(shb_batch *b);
+
+/* Outputs, valid after shb_wait until the next shb_submit on the same batch.
+ * shb_digests: n_records x shb_digest_size(algos[slot]) raw bytes in INPUT ORDER.  A record whose
+ * normalised length is 0 has an all-zero slot; the host prints "" for it (empty-sequence rule,
+ * seqhasher.go:292-295) by testing shb_out_lengths()[i] == 0.
+ * shb_out_lengths: post-normalisation length of each record.
+ * shb_out_offsets / shb_out_residues: with SHB_FLAG_EMIT_SEQ, the normalised sequences in CSR form
+ * (what the reference writes back to record.Seq.Seq at seqhasher.go:252 for full-record output). */
+const uint8_t *shb_digests(shb_batch *b, int slot);
+const int64_t *shb_out_lengths(shb_batch *b);
+const int64_t *shb_out_offsets(shb_batch *b);
+const uint8_t *shb_out_residues(shb_batch *b);
+
+/* ---- device-resident path (kernel-only timing, chaining after a GPU-side producer) ---- */
+
+/* Same computation with every buffer already in the memory of `device`, enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream).  d_residues must be 16-byte
+ * aligned and readable for 16 bytes past offsets[n]; d_digests[k] receives
+ * n x shb_digest_size(algos[k]) bytes; d_out_lengths may be NULL.  d_scratch (may be NULL unless
+ * SHB_FLAG_STRIP is set) must hold shb_scratch_bytes(total_bytes, n) bytes.  No host sync. */
+size_t shb_scratch_bytes(size_t total_bytes, size_t n_records);
+int shb_hash_device(int device, const uint8_t *d_residues, const int64_t *d_offsets, size_t n_records,
+                    size_t total_bytes, const int *algos, int n_algos, unsigned flags,
+                    uint8_t *const *d_digests, int64_t *d_out_lengths, void *d_scratch, void *stream);
+
+/* Number of kernels this library has launched in this process (monotone; for bench accounting). */
+unsigned long long shb_launch_count(void);
+
+/* ---- measurement helpers (not part of the hashing path) ---- */
+
+/* Deterministic synthetic residues written on the device: record i of fixed length `len` (or of
+ * length lens[i] when d_offsets != NULL) gets bases "ACGT"[2 bits] from splitmix64(seed, byte
+ * index); lower_permille of the bytes are lower-cased; n_permille become 'N'.  tests/ carries the
+ * identical numpy generator. */
+int shb_synth_fill(int device, uint8_t *d_residues, size_t total_bytes, uint64_t seed, unsigned lower_permille,
+                   unsigned n_permille, void *stream);
+
+/* Register-only integer throughput probes: kind 0 LOP3, 1 IADD3, 2 SHF, 3 IMAD, 4 PRMT,
+ * 5 the SHA-1 instruction mix (LOP3:IADD3:SHF:PRMT = 208:165:224:16),
+ * 6 LOP3+IMAD interleaved 1:1.  Returns lane-instructions per second, or <0. */
+double shb_probe_int_peak(int device, int kind, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

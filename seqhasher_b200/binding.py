@@ -1,0 +1,224 @@
+"""ctypes binding of libseqhash_b200.so (the C ABI in include/seqhash_b200.h).
+
+This is the only way Python reaches the CUDA kernels.  There is no fallback: if the shared
+library is missing the import of any compute entry point raises, and every call fails with the
+library's own error when no sm_100 GPU is usable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libseqhash_b200.so")
+
+ALGO_NAMES = ["sha1", "sha3", "md5", "xxhash", "xxh3", "cityhash", "murmur3", "nthash", "blake3", "k12",
+              "rapidhash", "rapidhash32"]
+DIGEST_SIZES = [20, 64, 16, 8, 8, 16, 16, 8, 32, 128, 8, 4]
+FLAG_UPPER = 1
+FLAG_STRIP = 2
+FLAG_EMIT_SEQ = 4
+
+# every symbol include/seqhash_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "shb_init", "shb_shutdown", "shb_last_error", "shb_version", "shb_algo_id", "shb_algo_name",
+    "shb_digest_size", "shb_batch_create", "shb_batch_create_on", "shb_batch_destroy", "shb_batch_residues",
+    "shb_batch_offsets", "shb_submit", "shb_wait", "shb_digests", "shb_out_lengths", "shb_out_offsets",
+    "shb_out_residues", "shb_scratch_bytes", "shb_hash_device", "shb_launch_count", "shb_synth_fill",
+    "shb_probe_int_peak",
+]
+
+
+class SeqhashError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library; raises if it has not been built (no CPU path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SeqhashError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). seqhasher_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    L.shb_init.argtypes = [c.c_int, c.c_int]; L.shb_init.restype = c.c_int
+    L.shb_shutdown.argtypes = []; L.shb_shutdown.restype = None
+    L.shb_last_error.argtypes = []; L.shb_last_error.restype = c.c_char_p
+    L.shb_version.argtypes = []; L.shb_version.restype = c.c_char_p
+    L.shb_algo_id.argtypes = [c.c_char_p]; L.shb_algo_id.restype = c.c_int
+    L.shb_algo_name.argtypes = [c.c_int]; L.shb_algo_name.restype = c.c_char_p
+    L.shb_digest_size.argtypes = [c.c_int]; L.shb_digest_size.restype = c.c_size_t
+    L.shb_batch_create.argtypes = [c.c_size_t, c.c_size_t]; L.shb_batch_create.restype = c.c_void_p
+    L.shb_batch_create_on.argtypes = [c.c_int, c.c_size_t, c.c_size_t]; L.shb_batch_create_on.restype = c.c_void_p
+    L.shb_batch_destroy.argtypes = [c.c_void_p]; L.shb_batch_destroy.restype = None
+    L.shb_batch_residues.argtypes = [c.c_void_p]; L.shb_batch_residues.restype = c.c_void_p
+    L.shb_batch_offsets.argtypes = [c.c_void_p]; L.shb_batch_offsets.restype = c.c_void_p
+    L.shb_submit.argtypes = [c.c_void_p, c.c_size_t, c.POINTER(c.c_int), c.c_int, c.c_uint]; L.shb_submit.restype = c.c_int
+    L.shb_wait.argtypes = [c.c_void_p]; L.shb_wait.restype = c.c_int
+    L.shb_digests.argtypes = [c.c_void_p, c.c_int]; L.shb_digests.restype = c.c_void_p
+    L.shb_out_lengths.argtypes = [c.c_void_p]; L.shb_out_lengths.restype = c.c_void_p
+    L.shb_out_offsets.argtypes = [c.c_void_p]; L.shb_out_offsets.restype = c.c_void_p
+    L.shb_out_residues.argtypes = [c.c_void_p]; L.shb_out_residues.restype = c.c_void_p
+    L.shb_scratch_bytes.argtypes = [c.c_size_t, c.c_size_t]; L.shb_scratch_bytes.restype = c.c_size_t
+    L.shb_hash_device.argtypes = [c.c_int, c.c_void_p, c.c_void_p, c.c_size_t, c.c_size_t, c.POINTER(c.c_int), c.c_int,
+                                  c.c_uint, c.POINTER(c.c_void_p), c.c_void_p, c.c_void_p, c.c_void_p]
+    L.shb_hash_device.restype = c.c_int
+    L.shb_launch_count.argtypes = []; L.shb_launch_count.restype = c.c_ulonglong
+    L.shb_synth_fill.argtypes = [c.c_int, c.c_void_p, c.c_size_t, c.c_uint64, c.c_uint, c.c_uint, c.c_void_p]
+    L.shb_synth_fill.restype = c.c_int
+    L.shb_probe_int_peak.argtypes = [c.c_int, c.c_int, c.c_int]; L.shb_probe_int_peak.restype = c.c_double
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str) -> None:
+    if rc < 0:
+        raise SeqhashError(f"{what} failed ({rc}): {lib().shb_last_error().decode()}")
+
+
+def init(n_gpus: int = 0) -> int:
+    rc = lib().shb_init(n_gpus, 0)
+    _check(rc, "shb_init")
+    return rc
+
+
+def algo_id(name: str) -> int:
+    return lib().shb_algo_id(name.encode())
+
+
+def _ids(algos) -> list[int]:
+    out = []
+    for a in algos:
+        i = a if isinstance(a, int) else algo_id(a)
+        if i < 0 or i >= len(ALGO_NAMES):
+            raise SeqhashError(f"unknown hash type {a!r}")
+        out.append(i)
+    return out
+
+
+class Batch:
+    """One shb_batch: pinned staging + device buffers + a stream.  Fill, submit, wait, read."""
+
+    def __init__(self, max_bytes: int, max_records: int, device: int = 0):
+        L = lib()
+        self._h = L.shb_batch_create_on(device, max_bytes, max_records)
+        if not self._h:
+            raise SeqhashError(f"shb_batch_create failed: {L.shb_last_error().decode()}")
+        self.max_bytes, self.max_records = max_bytes, max_records
+        rp = L.shb_batch_residues(self._h)
+        op = L.shb_batch_offsets(self._h)
+        self.residues = np.ctypeslib.as_array(ctypes.cast(rp, ctypes.POINTER(ctypes.c_uint8)), shape=(max_bytes + 16,))
+        self.offsets = np.ctypeslib.as_array(ctypes.cast(op, ctypes.POINTER(ctypes.c_int64)), shape=(max_records + 1,))
+        self.n = 0
+        self.algos: list[int] = []
+        self.flags = 0
+
+    def close(self) -> None:
+        if self._h:
+            lib().shb_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load(self, residues: np.ndarray, offsets: np.ndarray) -> None:
+        """Copy a CSR batch into the pinned staging buffers."""
+        n = len(offsets) - 1
+        total = int(offsets[-1]) if n >= 0 and len(offsets) else 0
+        if n > self.max_records or total > self.max_bytes:
+            raise SeqhashError("batch exceeds capacity")
+        self.residues[:total] = residues[:total]
+        self.offsets[: n + 1] = offsets
+        self.n = n
+
+    def submit(self, algos, flags: int, n: int | None = None) -> None:
+        if n is not None:
+            self.n = n
+        self.algos = _ids(algos)
+        self.flags = flags
+        arr = (ctypes.c_int * len(self.algos))(*self.algos)
+        _check(lib().shb_submit(self._h, self.n, arr, len(self.algos), flags), "shb_submit")
+
+    def wait(self) -> None:
+        _check(lib().shb_wait(self._h), "shb_wait")
+
+    def digests(self, slot: int) -> np.ndarray:
+        p = lib().shb_digests(self._h, slot)
+        ds = DIGEST_SIZES[self.algos[slot]]
+        if self.n == 0:
+            return np.zeros((0, ds), dtype=np.uint8)
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(self.n, ds))
+
+    def out_lengths(self) -> np.ndarray:
+        p = lib().shb_out_lengths(self._h)
+        if self.n == 0:
+            return np.zeros(0, dtype=np.int64)
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_int64)), shape=(self.n,))
+
+    def out_sequences(self):
+        """(residues, offsets) of the normalised sequences; needs FLAG_EMIT_SEQ."""
+        po, pr = lib().shb_out_offsets(self._h), lib().shb_out_residues(self._h)
+        if not po or not pr:
+            raise SeqhashError("submit with FLAG_EMIT_SEQ to get the normalised sequences")
+        offs = np.ctypeslib.as_array(ctypes.cast(po, ctypes.POINTER(ctypes.c_int64)), shape=(self.n + 1,))
+        total = int(offs[self.n])
+        res = np.ctypeslib.as_array(ctypes.cast(pr, ctypes.POINTER(ctypes.c_uint8)), shape=(max(total, 1),))[:total]
+        return res, offs
+
+
+def hash_batch(residues: np.ndarray, offsets: np.ndarray, algos, flags: int, device: int = 0, emit: bool = False):
+    """Convenience one-shot through the host-buffer path: returns ([n x size uint8], lengths[, (res, offs)])."""
+    residues = np.ascontiguousarray(residues, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    b = Batch(max(int(offsets[-1]), 1), max(n, 1), device)
+    try:
+        b.load(residues, offsets)
+        b.submit(algos, flags | (FLAG_EMIT_SEQ if emit else 0))
+        b.wait()
+        outs = [b.digests(k).copy() for k in range(len(b.algos))]
+        lens = b.out_lengths().copy()
+        if emit:
+            r, o = b.out_sequences()
+            return outs, lens, (r.copy(), o.copy())
+        return outs, lens
+    finally:
+        b.close()
+
+
+def hash_device(d_residues, d_offsets, n: int, total_bytes: int, algos, flags: int, d_digests, d_out_lengths=None,
+                d_scratch=None, stream: int = 0, device: int = 0) -> None:
+    """Device-resident path: arguments are raw device pointers (ints), e.g. torch tensors' data_ptr()."""
+    ids = _ids(algos)
+    arr = (ctypes.c_int * len(ids))(*ids)
+    ptrs = (ctypes.c_void_p * len(ids))(*d_digests)
+    _check(lib().shb_hash_device(device, d_residues, d_offsets, n, total_bytes, arr, len(ids), flags, ptrs,
+                                 d_out_lengths, d_scratch, stream), "shb_hash_device")
+
+
+def scratch_bytes(total_bytes: int, n: int) -> int:
+    return lib().shb_scratch_bytes(total_bytes, n)
+
+
+def synth_fill(d_residues: int, total_bytes: int, seed: int, lower_permille: int = 0, n_permille: int = 0,
+               stream: int = 0, device: int = 0) -> None:
+    _check(lib().shb_synth_fill(device, d_residues, total_bytes, seed & 0xFFFFFFFFFFFFFFFF, lower_permille, n_permille,
+                                stream), "shb_synth_fill")
+
+
+def launch_count() -> int:
+    return lib().shb_launch_count()
+
+
+def probe_int_peak(kind: int, iters: int = 2000, device: int = 0) -> float:
+    return lib().shb_probe_int_peak(device, kind, iters)

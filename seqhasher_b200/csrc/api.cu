@@ -1,0 +1,366 @@
+// api.cu — the C ABI of include/seqhash_b200.h: device selection, batch objects (pinned staging,
+// device buffers, one stream each), the submit/wait pipeline and the device-resident entry point.
+// There is no CPU fallback anywhere in this file: without a usable sm_100 device every call fails.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/seqhash_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string t_err;
+std::mutex g_mu;
+int g_ndev = 0;   // devices 0..g_ndev-1 in use; 0 = not initialised
+
+int fail(int code, const std::string &msg)
+{
+    t_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(SHB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                          \
+    do {                                                  \
+        cudaError_t e_ = (call);                          \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+const char *const kNames[SHB_N_ALGOS] = {"sha1", "sha3", "md5", "xxhash", "xxh3", "cityhash",
+                                         "murmur3", "nthash", "blake3", "k12", "rapidhash", "rapidhash32"};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// scratch layout of the normalise pre-pass inside one allocation
+struct ScratchLayout {
+    size_t res_off, offs_off, counts_off, prefix_off, total;
+    ScratchLayout(size_t total_bytes, size_t n)
+    {
+        const size_t nb = shb::norm_blocks(total_bytes);
+        res_off = 0;
+        offs_off = align_up(total_bytes + 32, 256);
+        counts_off = offs_off + align_up((n + 1) * sizeof(int64_t), 256);
+        prefix_off = counts_off + align_up(nb * sizeof(uint32_t), 256);
+        total = prefix_off + align_up((nb + 1) * sizeof(int64_t), 256);
+    }
+};
+
+// The hashing pipeline on device-resident buffers; shared by shb_submit and shb_hash_device.
+int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t total_bytes, const int *algos,
+                 int n_algos, unsigned flags, uint8_t *const *d_digests, int64_t *d_out_len, void *d_scratch,
+                 cudaStream_t st, const uint8_t **norm_res, const int64_t **norm_offs)
+{
+    const bool upper = flags & SHB_FLAG_UPPER, strip = flags & SHB_FLAG_STRIP, emit = flags & SHB_FLAG_EMIT_SEQ;
+    const uint8_t *res = d_res;
+    const int64_t *offs = d_offs;
+    bool fused_upper = upper;
+    if (strip || emit) {
+        if (!d_scratch) return fail(SHB_ERR_BAD_ARG, "SHB_FLAG_STRIP/EMIT_SEQ need a scratch buffer");
+        ScratchLayout L(total_bytes, n);
+        uint8_t *base = static_cast<uint8_t *>(d_scratch);
+        uint8_t *o_res = base + L.res_off;
+        int64_t *o_offs = reinterpret_cast<int64_t *>(base + L.offs_off);
+        CU(shb::launch_normalise(d_res, d_offs, n, total_bytes, strip, upper,
+                                 reinterpret_cast<uint32_t *>(base + L.counts_off),
+                                 reinterpret_cast<int64_t *>(base + L.prefix_off), o_res, o_offs, d_out_len, st));
+        res = o_res;
+        offs = o_offs;
+        fused_upper = false;   // already applied while compacting
+    } else if (d_out_len) {
+        CU(shb::launch_lengths(d_offs, n, d_out_len, st));
+    }
+    if (norm_res) *norm_res = res;
+    if (norm_offs) *norm_offs = offs;
+    for (int k = 0; k < n_algos; k++) {
+        // identical algo requested twice: compute once, copy the slot (the reference recomputes)
+        int prev = -1;
+        for (int j = 0; j < k; j++)
+            if (algos[j] == algos[k]) { prev = j; break; }
+        if (prev >= 0) {
+            CU(cudaMemcpyAsync(d_digests[k], d_digests[prev], n * shb::digest_size(algos[k]),
+                               cudaMemcpyDeviceToDevice, st));
+            continue;
+        }
+        CU(shb::launch_hash_direct(algos[k], fused_upper, res, offs, n, d_digests[k], st));
+    }
+    return SHB_OK;
+}
+
+int check_algos(const int *algos, int n_algos)
+{
+    if (n_algos < 0 || (n_algos > 0 && !algos)) return fail(SHB_ERR_BAD_ARG, "bad algo list");
+    for (int k = 0; k < n_algos; k++)
+        if (algos[k] < 0 || algos[k] >= SHB_N_ALGOS) return fail(SHB_ERR_BAD_ARG, "algo id out of range");
+    return SHB_OK;
+}
+
+}  // namespace
+
+struct shb_batch {
+    int device = 0;
+    size_t max_bytes = 0, max_records = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t *h_res = nullptr, *d_res = nullptr;
+    int64_t *h_offs = nullptr, *d_offs = nullptr;
+    // outputs, grown on demand
+    uint8_t *h_dig = nullptr, *d_dig = nullptr;
+    size_t dig_cap = 0;
+    int64_t *h_len = nullptr, *d_len = nullptr;   // max_records
+    void *d_scratch = nullptr;
+    size_t scratch_cap = 0;
+    uint8_t *h_out_res = nullptr;
+    int64_t *h_out_offs = nullptr;
+    // state of the last submit
+    size_t n = 0;
+    unsigned flags = 0;
+    std::vector<int> algos;
+    std::vector<size_t> slot_off;
+    bool lengths_on_device = false, lengths_valid = false;
+};
+
+extern "C" {
+
+int shb_init(int n_gpus, int flags)
+{
+    (void)flags;
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(SHB_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0"));
+    int want = n_gpus <= 0 ? count : n_gpus;
+    if (want > count) return fail(SHB_ERR_NO_DEVICE, "fewer CUDA devices than requested");
+    for (int d = 0; d < want; d++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) != cudaSuccess || p.major != 10)
+            return fail(SHB_ERR_NO_DEVICE, "device is not sm_100 (Blackwell B200); this library has no other code path");
+    }
+    g_ndev = want;
+    return want;
+}
+
+void shb_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_ndev = 0;
+}
+
+const char *shb_last_error(void) { return t_err.c_str(); }
+const char *shb_version(void) { return "seqhash_b200 0.1.0 (sm_100a)"; }
+
+int shb_algo_id(const char *name)
+{
+    if (!name) return -1;
+    for (int i = 0; i < SHB_N_ALGOS; i++)
+        if (std::strcmp(name, kNames[i]) == 0) return i;
+    return -1;
+}
+const char *shb_algo_name(int algo) { return (algo >= 0 && algo < SHB_N_ALGOS) ? kNames[algo] : nullptr; }
+size_t shb_digest_size(int algo) { return (algo >= 0 && algo < SHB_N_ALGOS) ? (size_t)shb::digest_size(algo) : 0; }
+
+unsigned long long shb_launch_count(void) { return shb::g_launches; }
+
+size_t shb_scratch_bytes(size_t total_bytes, size_t n_records) { return ScratchLayout(total_bytes, n_records).total; }
+
+shb_batch *shb_batch_create_on(int device, size_t max_bytes, size_t max_records)
+{
+    if (g_ndev == 0 && shb_init(0, 0) < 0) return nullptr;
+    if (device < 0 || device >= g_ndev) {
+        fail(SHB_ERR_BAD_ARG, "device not selected by shb_init");
+        return nullptr;
+    }
+    if (max_bytes >= ((size_t)1 << 40) || max_records >= ((size_t)1 << 32)) {
+        fail(SHB_ERR_BAD_ARG, "batch capacity too large");
+        return nullptr;
+    }
+    shb_batch *b = new shb_batch();
+    b->device = device;
+    b->max_bytes = max_bytes;
+    b->max_records = max_records;
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaHostAlloc(&b->h_res, max_bytes + 32, cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc(&b->h_offs, (max_records + 1) * sizeof(int64_t), cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc(&b->h_len, (max_records + 1) * sizeof(int64_t), cudaHostAllocDefault) == cudaSuccess &&
+              cudaMalloc(&b->d_res, max_bytes + 32) == cudaSuccess &&
+              cudaMalloc(&b->d_offs, (max_records + 1) * sizeof(int64_t)) == cudaSuccess &&
+              cudaMalloc(&b->d_len, (max_records + 1) * sizeof(int64_t)) == cudaSuccess;
+    if (!ok) {
+        fail(SHB_ERR_CUDA, std::string("batch allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+        shb_batch_destroy(b);
+        return nullptr;
+    }
+    b->h_offs[0] = 0;
+    return b;
+}
+
+shb_batch *shb_batch_create(size_t max_bytes, size_t max_records) { return shb_batch_create_on(0, max_bytes, max_records); }
+
+void shb_batch_destroy(shb_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
+    cudaFreeHost(b->h_res); cudaFreeHost(b->h_offs); cudaFreeHost(b->h_len); cudaFreeHost(b->h_dig);
+    cudaFreeHost(b->h_out_res); cudaFreeHost(b->h_out_offs);
+    cudaFree(b->d_res); cudaFree(b->d_offs); cudaFree(b->d_len); cudaFree(b->d_dig); cudaFree(b->d_scratch);
+    delete b;
+}
+
+uint8_t *shb_batch_residues(shb_batch *b) { return b ? b->h_res : nullptr; }
+int64_t *shb_batch_offsets(shb_batch *b) { return b ? b->h_offs : nullptr; }
+
+int shb_submit(shb_batch *b, size_t n, const int *algos, int n_algos, unsigned flags)
+{
+    if (!b) return fail(SHB_ERR_BAD_ARG, "null batch");
+    if (int rc = check_algos(algos, n_algos)) return rc;
+    if (n > b->max_records) return fail(SHB_ERR_CAPACITY, "more records than the batch capacity");
+    if (b->h_offs[0] != 0) return fail(SHB_ERR_OFFSETS, "offsets[0] must be 0");
+    // offsets must be monotone and each record shorter than 2^31 bytes (one pass over n+1 words)
+    int64_t prev = 0;
+    for (size_t i = 1; i <= n; i++) {
+        const int64_t cur = b->h_offs[i];
+        if (cur < prev || cur - prev > 0x7FFFFFFFLL) return fail(SHB_ERR_OFFSETS, "offsets not monotone or record >= 2^31 bytes");
+        prev = cur;
+    }
+    const size_t total = (size_t)prev;
+    if (total > b->max_bytes) return fail(SHB_ERR_CAPACITY, "more residue bytes than the batch capacity");
+    CU(cudaSetDevice(b->device));
+    // outputs
+    b->algos.assign(algos, algos + n_algos);
+    b->slot_off.assign(n_algos + 1, 0);
+    for (int k = 0; k < n_algos; k++) b->slot_off[k + 1] = b->slot_off[k] + align_up(n * shb::digest_size(algos[k]), 256);
+    const size_t need = b->slot_off[n_algos];
+    if (need > b->dig_cap) {
+        CU(cudaStreamSynchronize(b->stream));
+        cudaFreeHost(b->h_dig); cudaFree(b->d_dig);
+        b->h_dig = nullptr; b->d_dig = nullptr; b->dig_cap = 0;
+        CU(cudaHostAlloc(&b->h_dig, need, cudaHostAllocDefault));
+        CU(cudaMalloc(&b->d_dig, need));
+        b->dig_cap = need;
+    }
+    const bool norm = flags & (SHB_FLAG_STRIP | SHB_FLAG_EMIT_SEQ);
+    if (norm) {
+        const size_t sneed = ScratchLayout(b->max_bytes, b->max_records).total;
+        if (sneed > b->scratch_cap) {
+            CU(cudaStreamSynchronize(b->stream));
+            cudaFree(b->d_scratch);
+            b->d_scratch = nullptr; b->scratch_cap = 0;
+            CU(cudaMalloc(&b->d_scratch, sneed));
+            b->scratch_cap = sneed;
+        }
+        if ((flags & SHB_FLAG_EMIT_SEQ) && !b->h_out_res) {
+            CU(cudaHostAlloc(&b->h_out_res, b->max_bytes + 32, cudaHostAllocDefault));
+            CU(cudaHostAlloc(&b->h_out_offs, (b->max_records + 1) * sizeof(int64_t), cudaHostAllocDefault));
+        }
+    }
+    b->n = n;
+    b->flags = flags;
+    b->lengths_on_device = norm;
+    b->lengths_valid = false;
+    // H2D (the 16 pad bytes past `total` travel too so device readers never see stale bytes)
+    std::memset(b->h_res + total, 0, 32);
+    CU(cudaMemcpyAsync(b->d_res, b->h_res, align_up(total + 16, 16), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->d_offs, b->h_offs, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, b->stream));
+    std::vector<uint8_t *> d_slots(n_algos);
+    for (int k = 0; k < n_algos; k++) d_slots[k] = b->d_dig + b->slot_off[k];
+    const uint8_t *norm_res = nullptr;
+    const int64_t *norm_offs = nullptr;
+    if (int rc = run_pipeline(b->d_res, b->d_offs, n, total, algos, n_algos, flags, d_slots.data(),
+                              norm ? b->d_len : nullptr, b->d_scratch, b->stream, &norm_res, &norm_offs))
+        return rc;
+    // D2H
+    if (need) CU(cudaMemcpyAsync(b->h_dig, b->d_dig, need, cudaMemcpyDeviceToHost, b->stream));
+    if (norm) CU(cudaMemcpyAsync(b->h_len, b->d_len, n * sizeof(int64_t), cudaMemcpyDeviceToHost, b->stream));
+    if (flags & SHB_FLAG_EMIT_SEQ) {
+        CU(cudaMemcpyAsync(b->h_out_offs, norm_offs, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, b->stream));
+        // normalised residues are never longer than the input
+        CU(cudaMemcpyAsync(b->h_out_res, norm_res, align_up(total, 16), cudaMemcpyDeviceToHost, b->stream));
+    }
+    return SHB_OK;
+}
+
+int shb_wait(shb_batch *b)
+{
+    if (!b) return fail(SHB_ERR_BAD_ARG, "null batch");
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    return SHB_OK;
+}
+
+const uint8_t *shb_digests(shb_batch *b, int slot)
+{
+    if (!b || slot < 0 || slot >= (int)b->algos.size()) return nullptr;
+    return b->h_dig + b->slot_off[slot];
+}
+
+const int64_t *shb_out_lengths(shb_batch *b)
+{
+    if (!b) return nullptr;
+    if (!b->lengths_on_device && !b->lengths_valid) {   // nothing was stripped: lengths are the input's
+        for (size_t i = 0; i < b->n; i++) b->h_len[i] = b->h_offs[i + 1] - b->h_offs[i];
+        b->lengths_valid = true;
+    }
+    return b->h_len;
+}
+
+const int64_t *shb_out_offsets(shb_batch *b) { return (b && (b->flags & SHB_FLAG_EMIT_SEQ)) ? b->h_out_offs : nullptr; }
+const uint8_t *shb_out_residues(shb_batch *b) { return (b && (b->flags & SHB_FLAG_EMIT_SEQ)) ? b->h_out_res : nullptr; }
+
+int shb_hash_device(int device, const uint8_t *d_residues, const int64_t *d_offsets, size_t n_records,
+                    size_t total_bytes, const int *algos, int n_algos, unsigned flags, uint8_t *const *d_digests,
+                    int64_t *d_out_lengths, void *d_scratch, void *stream)
+{
+    if (g_ndev == 0 && shb_init(0, 0) < 0) return SHB_ERR_NO_DEVICE;
+    if (device < 0 || device >= g_ndev) return fail(SHB_ERR_BAD_ARG, "device not selected by shb_init");
+    if (int rc = check_algos(algos, n_algos)) return rc;
+    if ((reinterpret_cast<uintptr_t>(d_residues) & 15u) != 0) return fail(SHB_ERR_BAD_ARG, "d_residues must be 16-byte aligned");
+    if (n_records >= ((size_t)1 << 32)) return fail(SHB_ERR_BAD_ARG, "too many records");
+    CU(cudaSetDevice(device));
+    return run_pipeline(d_residues, d_offsets, n_records, total_bytes, algos, n_algos, flags, d_digests,
+                        d_out_lengths, d_scratch, static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+int shb_synth_fill(int device, uint8_t *d_residues, size_t total_bytes, uint64_t seed, unsigned lower_permille,
+                   unsigned n_permille, void *stream)
+{
+    if (g_ndev == 0 && shb_init(0, 0) < 0) return SHB_ERR_NO_DEVICE;
+    CU(cudaSetDevice(device));
+    CU(shb::launch_synth_fill(d_residues, total_bytes, seed, lower_permille, n_permille, static_cast<cudaStream_t>(stream)));
+    return SHB_OK;
+}
+
+double shb_probe_int_peak(int device, int kind, int iters)
+{
+    if (g_ndev == 0 && shb_init(0, 0) < 0) return -1.0;
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    uint32_t *sink = nullptr;
+    cudaEvent_t e0, e1;
+    if (cudaMalloc(&sink, 64) != cudaSuccess) return -1.0;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double lane_instr = 0;
+    double best = -1.0;
+    for (int rep = 0; rep < 4; rep++) {   // rep 0 warms up
+        cudaEventRecord(e0, 0);
+        if (shb::launch_probe(kind, iters, sink, &lane_instr, 0) != cudaSuccess) { best = -1.0; break; }
+        cudaEventRecord(e1, 0);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double rate = lane_instr / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}
+
+}  // extern "C"

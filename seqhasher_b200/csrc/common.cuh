@@ -1,0 +1,137 @@
+// common.cuh — device helpers shared by every hash kernel (sm_100a).
+//
+// A "reader" presents one record as little-endian words at arbitrary byte offsets, because
+// records sit at arbitrary byte positions of the CSR residue buffer (record.Seq.Seq of
+// seqhasher.go:241).  Two readers exist:
+//   GlobalReader<UPPER>  — straight from HBM/L2/L1 (direct path; upper-casing fused in the load,
+//                          seqhasher.go:249-251)
+//   SmemReader           — from a shared-memory tile that was staged by bulk async copy and
+//                          upper-cased in place once per tile
+// Both return words by funnel-shifting two aligned 32-bit loads, so no unaligned access is ever
+// issued; both may read (never use) up to 7 bytes past the record end, which the buffers pad.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace shb {
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int r) { return __funnelshift_r(x, x, r); }
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t rotr64(uint64_t x, int r) { return (x >> r) | (x << (64 - r)); }
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+__device__ __forceinline__ uint64_t bswap64(uint64_t x)
+{
+    return ((uint64_t)bswap32((uint32_t)x) << 32) | bswap32((uint32_t)(x >> 32));
+}
+__device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+// lo64(a*b) ^ hi64(a*b): the "fold" of xxh3 / rapidhash
+__device__ __forceinline__ uint64_t mulfold64(uint64_t a, uint64_t b) { return (a * b) ^ __umul64hi(a, b); }
+
+// ASCII upper-casing of 4 packed bytes (a-z -> A-Z, everything else untouched, bytes >= 0x80 too).
+__device__ __forceinline__ uint32_t upper4(uint32_t x)
+{
+    uint32_t y = x & 0x7f7f7f7fu;
+    uint32_t ge_a = y + 0x1f1f1f1fu;   // bit7 set  <=>  (b & 0x7f) >= 'a'
+    uint32_t gt_z = y + 0x05050505u;   // bit7 set  <=>  (b & 0x7f) >  'z'
+    uint32_t m = ge_a & ~gt_z & ~x & 0x80808080u;
+    return x ^ (m >> 2);
+}
+
+// reference whitespace set for ASCII input (bytes.Fields fast path, seqhasher.go:246)
+__device__ __forceinline__ bool is_ws(uint32_t c) { return c == 0x20u || (c - 9u) <= 4u; }
+
+template <bool UPPER>
+struct GlobalReader {
+    const uint32_t *w;   // aligned-down word pointer of the record start
+    uint32_t bo;         // start & 3
+    uint32_t sh;         // bo * 8
+    __device__ __forceinline__ GlobalReader(const uint8_t *base, int64_t start)
+    {
+        uintptr_t a = (uintptr_t)base + (uintptr_t)start;
+        w = (const uint32_t *)(a & ~(uintptr_t)3);
+        bo = (uint32_t)(a & 3);
+        sh = bo * 8;
+    }
+    // 32-bit LE word at byte offset `off` (multiple of 4) of the record
+    __device__ __forceinline__ uint32_t u32(uint32_t off) const
+    {
+        const uint32_t *q = w + (off >> 2);
+        uint32_t v = __funnelshift_r(__ldg(q), __ldg(q + 1), sh);
+        return UPPER ? upper4(v) : v;
+    }
+    // 32-bit LE word at ANY byte offset
+    __device__ __forceinline__ uint32_t u32x(uint32_t off) const
+    {
+        uint32_t a = off + bo;
+        const uint32_t *q = w + (a >> 2);
+        uint32_t v = __funnelshift_r(__ldg(q), __ldg(q + 1), (a & 3) * 8);
+        return UPPER ? upper4(v) : v;
+    }
+    __device__ __forceinline__ uint64_t u64(uint32_t off) const { return mk64(u32(off), u32(off + 4)); }
+    __device__ __forceinline__ uint64_t u64x(uint32_t off) const
+    {
+        uint32_t a = off + bo;
+        const uint32_t *q = w + (a >> 2);
+        uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+        uint32_t s = (a & 3) * 8;
+        uint32_t lo = __funnelshift_r(w0, w1, s), hi = __funnelshift_r(w1, w2, s);
+        if (UPPER) { lo = upper4(lo); hi = upper4(hi); }
+        return mk64(lo, hi);
+    }
+    __device__ __forceinline__ uint32_t u8(uint32_t off) const { return u32x(off) & 0xffu; }
+};
+
+struct SmemReader {
+    const uint32_t *w;
+    uint32_t bo, sh;
+    __device__ __forceinline__ SmemReader(const uint8_t *tile, uint32_t start)
+    {
+        w = (const uint32_t *)(tile + (start & ~3u));
+        bo = start & 3u;
+        sh = bo * 8;
+    }
+    __device__ __forceinline__ uint32_t u32(uint32_t off) const
+    {
+        const uint32_t *q = w + (off >> 2);
+        return __funnelshift_r(q[0], q[1], sh);
+    }
+    __device__ __forceinline__ uint32_t u32x(uint32_t off) const
+    {
+        uint32_t a = off + bo;
+        const uint32_t *q = w + (a >> 2);
+        return __funnelshift_r(q[0], q[1], (a & 3) * 8);
+    }
+    __device__ __forceinline__ uint64_t u64(uint32_t off) const { return mk64(u32(off), u32(off + 4)); }
+    __device__ __forceinline__ uint64_t u64x(uint32_t off) const
+    {
+        uint32_t a = off + bo;
+        const uint32_t *q = w + (a >> 2);
+        uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+        uint32_t s = (a & 3) * 8;
+        return mk64(__funnelshift_r(w0, w1, s), __funnelshift_r(w1, w2, s));
+    }
+    __device__ __forceinline__ uint32_t u8(uint32_t off) const { return u32x(off) & 0xffu; }
+};
+
+// Word `off` (multiple of 4) of the record as a padded Merkle–Damgard / sponge tail: bytes at or
+// past `len` read as zero except the pad byte `pad` placed at position len.
+template <class R>
+__device__ __forceinline__ uint32_t padded_u32(const R &r, uint32_t off, uint32_t len, uint32_t pad)
+{
+    if (off + 4 <= len) return r.u32(off);
+    if (off > len) return 0;
+    uint32_t k = len - off;                       // 0..3 valid bytes
+    uint32_t raw = k ? r.u32(off) : 0;
+    uint32_t keep = (1u << (8 * k)) - 1u;         // k == 0 -> 0
+    return (raw & keep) | (pad << (8 * k));
+}
+
+// big-endian stores of word hashes ("%016x" / "%08x" order)
+__device__ __forceinline__ void store_be64(uint8_t *out, uint64_t v)
+{
+    uint2 t = make_uint2(bswap32((uint32_t)(v >> 32)), bswap32((uint32_t)v));
+    *reinterpret_cast<uint2 *>(out) = t;
+}
+
+}  // namespace shb

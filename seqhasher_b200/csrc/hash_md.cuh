@@ -1,0 +1,119 @@
+// hash_md.cuh — SHA-1 and MD5 device hashers (64-byte-block Merkle–Damgard family).
+//
+// Replaces crypto/sha1.Sum (seqhasher.go:299-301) and crypto/md5.Sum (seqhasher.go:305-307).
+// One thread walks one record: the 80 (64) rounds are fully unrolled over a rolling 16-word
+// schedule held in registers; data blocks and the padded tail go through the same single inlined
+// compress so the instruction footprint stays one block body.  Integer-pipe bound: the work per
+// block is fixed (SHA-1: 613 fused int ops).
+#pragma once
+#include "common.cuh"
+
+namespace shb {
+
+__device__ __forceinline__ void sha1_compress(uint32_t (&h)[5], uint32_t (&w)[16])
+{
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
+#pragma unroll
+    for (int t = 0; t < 80; t++) {
+        uint32_t wt;
+        if (t < 16) {
+            wt = w[t];
+        } else {
+            wt = rotl32(w[(t - 3) & 15] ^ w[(t - 8) & 15] ^ w[(t - 14) & 15] ^ w[t & 15], 1);
+            w[t & 15] = wt;
+        }
+        uint32_t f, k;
+        if (t < 20) { f = (b & c) | (~b & d); k = 0x5A827999u; }
+        else if (t < 40) { f = b ^ c ^ d; k = 0x6ED9EBA1u; }
+        else if (t < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8F1BBCDCu; }
+        else { f = b ^ c ^ d; k = 0xCA62C1D6u; }
+        uint32_t tmp = rotl32(a, 5) + f + e + k + wt;
+        e = d; d = c; c = rotl32(b, 30); b = a; a = tmp;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
+}
+
+// out: 20 bytes, 4-byte aligned
+template <class R>
+__device__ __forceinline__ void sha1_record(const R &r, uint32_t len, uint8_t *out)
+{
+    uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
+    const uint32_t nblocks = (len + 9 + 63) >> 6;   // len <= 2^32-1-72 guaranteed by the caller
+    for (uint32_t blk = 0; blk < nblocks; blk++) {
+        const uint32_t base = blk << 6;
+        uint32_t w[16];
+        if (base + 64 <= len) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = bswap32(r.u32(base + 4 * i));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = bswap32(padded_u32(r, base + 4 * i, len, 0x80u));
+            if (blk == nblocks - 1) {
+                w[14] = len >> 29;
+                w[15] = len << 3;
+            }
+        }
+        sha1_compress(h, w);
+    }
+    uint32_t *o = reinterpret_cast<uint32_t *>(out);
+#pragma unroll
+    for (int i = 0; i < 5; i++) o[i] = bswap32(h[i]);
+}
+
+__device__ __forceinline__ void md5_compress(uint32_t (&h)[4], const uint32_t (&m)[16])
+{
+    constexpr uint32_t K[64] = {
+        0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
+        0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
+        0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
+        0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
+        0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
+        0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
+        0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
+        0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+    constexpr int S[4][4] = {{7, 12, 17, 22}, {5, 9, 14, 20}, {4, 11, 16, 23}, {6, 10, 15, 21}};
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        uint32_t f;
+        int g;
+        if (i < 16) { f = (b & c) | (~b & d); g = i; }
+        else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+        else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+        else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+        uint32_t t = d;
+        d = c; c = b;
+        b = b + rotl32(a + f + K[i] + m[g], S[i >> 4][i & 3]);
+        a = t;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d;
+}
+
+// out: 16 bytes, 4-byte aligned
+template <class R>
+__device__ __forceinline__ void md5_record(const R &r, uint32_t len, uint8_t *out)
+{
+    uint32_t h[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+    const uint32_t nblocks = (len + 9 + 63) >> 6;
+    for (uint32_t blk = 0; blk < nblocks; blk++) {
+        const uint32_t base = blk << 6;
+        uint32_t m[16];
+        if (base + 64 <= len) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) m[i] = r.u32(base + 4 * i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) m[i] = padded_u32(r, base + 4 * i, len, 0x80u);
+            if (blk == nblocks - 1) {
+                m[14] = len << 3;
+                m[15] = len >> 29;
+            }
+        }
+        md5_compress(h, m);
+    }
+    uint32_t *o = reinterpret_cast<uint32_t *>(out);
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = h[i];
+}
+
+}  // namespace shb

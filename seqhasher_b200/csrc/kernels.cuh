@@ -1,0 +1,45 @@
+// kernels.cuh — host-callable launchers of the sm_100a kernels (internal to libseqhash_b200).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace shb {
+
+constexpr int N_ALGOS = 12;
+enum Algo : int {
+    A_SHA1 = 0, A_SHA3 = 1, A_MD5 = 2, A_XXHASH = 3, A_XXH3 = 4, A_CITYHASH = 5, A_MURMUR3 = 6,
+    A_NTHASH = 7, A_BLAKE3 = 8, A_K12 = 9, A_RAPIDHASH = 10, A_RAPIDHASH32 = 11
+};
+__host__ __device__ constexpr int digest_size(int a)
+{
+    constexpr int S[N_ALGOS] = {20, 64, 16, 8, 8, 16, 16, 8, 32, 128, 8, 4};
+    return S[a];
+}
+
+extern unsigned long long g_launches;   // kernels launched by this library (host counter)
+
+// Byte blocks of the normalise pre-pass.
+constexpr uint32_t NORM_BLK = 4096;
+inline size_t norm_blocks(size_t total_bytes) { return total_bytes / NORM_BLK + 1; }
+
+// Direct path: one thread per record straight from global memory.
+cudaError_t launch_hash_direct(int algo, bool upper, const uint8_t *res, const int64_t *offs, size_t n,
+                               uint8_t *out, cudaStream_t st);
+
+// Normalise pre-pass (seqhasher.go:246-251 materialised): whitespace strip (if strip) + upper-casing
+// (if upper) of the whole CSR batch into out_res / out_offs (n+1) / out_len (n, may be null).
+// block_counts: norm_blocks() uint32; block_prefix: norm_blocks()+1 int64.
+cudaError_t launch_normalise(const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes, bool strip,
+                             bool upper, uint32_t *block_counts, int64_t *block_prefix, uint8_t *out_res,
+                             int64_t *out_offs, int64_t *out_len, cudaStream_t st);
+
+cudaError_t launch_lengths(const int64_t *offs, size_t n, int64_t *out_len, cudaStream_t st);
+
+cudaError_t launch_synth_fill(uint8_t *res, size_t total_bytes, uint64_t seed, unsigned lower_permille,
+                              unsigned n_permille, cudaStream_t st);
+
+// returns lane-instructions executed; elapsed time measured by the caller
+cudaError_t launch_probe(int kind, int iters, uint32_t *sink, double *lane_instr, cudaStream_t st);
+
+}  // namespace shb

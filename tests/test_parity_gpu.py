@@ -1,0 +1,133 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact, on the reference's golden
+inputs, on every block/stripe/chunk boundary length, on ragged and empty records, and in both case modes."""
+import numpy as np
+import pytest
+
+import golden_vectors as G
+from synth import BOUNDARY_LENGTHS, csr_from_lengths, csr_from_records
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["sha1", "sha3", "md5", "xxhash", "xxh3", "cityhash", "murmur3", "nthash", "blake3", "k12", "rapidhash",
+       "rapidhash32"]
+
+
+@pytest.fixture(scope="module")
+def shb():
+    from seqhasher_b200 import binding
+    binding.init(1)
+    return binding
+
+
+def _hex(d, lens):
+    return [row.tobytes().hex() if n else "" for row, n in zip(d, lens)]
+
+
+def test_reference_goldens_through_cabi(shb):
+    recs = [b"ACTG", b"TGCA", b"AAAA", b"aaaa", b"ACTGINVALID", b"actg"]
+    res, offs = csr_from_records(recs)
+    outs, lens = shb.hash_batch(res, offs, ALL, flags=0)
+    for k, a in enumerate(ALL):
+        assert _hex(outs[k], lens)[0] == G.ACTG[a], a
+    for a, data, want, cite in G.EXTRA:
+        if data in recs:
+            got = _hex(outs[ALL.index(a)], lens)[recs.index(data)]
+            assert got.startswith(want), (a, cite)
+    # default mode upper-cases (seqhasher.go:249-251): "actg" and "aaaa" hash like their upper-case forms
+    outs_u, lens_u = shb.hash_batch(res, offs, ALL, flags=shb.FLAG_UPPER)
+    for k, a in enumerate(ALL):
+        h = _hex(outs_u[k], lens_u)
+        assert h[5] == G.ACTG[a] and h[3] == h[2], a
+
+
+def test_long_sequence_goldens(shb):
+    # test/test2_binary.sh:148-169
+    res, offs = csr_from_records([b"ACTG" * 25000, b"A" * 100000])
+    outs, lens = shb.hash_batch(res, offs, ["sha1"], flags=shb.FLAG_UPPER)
+    assert _hex(outs[0], lens) == ["3200abf5034212fb5d90fa242fc1cea5e0f3dd00", "e27b41eb7f7370b36f1b2fa63f05652f52423277"]
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["casesensitive", "upper"])
+def test_boundary_lengths_all_algorithms(shb, oracle, flags):
+    res, offs = csr_from_lengths(BOUNDARY_LENGTHS, seed=0xB200, lower_permille=250, n_permille=20)
+    want, wl = oracle.batch(res, offs, ALL, flags=flags, threads=8)
+    got, gl = shb.hash_batch(res, offs, ALL, flags=flags)
+    assert (gl == wl).all()
+    for k, a in enumerate(ALL):
+        bad = np.nonzero((got[k] != want[k]).any(axis=1))[0]
+        assert bad.size == 0, f"{a}: mismatch at lengths {[BOUNDARY_LENGTHS[i] for i in bad[:8]]}"
+
+
+def test_arbitrary_bytes_and_alignments(shb, oracle):
+    # non-DNA bytes are hashed as-is (seqhasher_test.go:817-834); every start alignment 0..15 occurs
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 700, size=4000)
+    offs = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    res = rng.integers(0, 256, size=int(offs[-1]), dtype=np.uint8)
+    for flags in (0, 1):
+        want, _ = oracle.batch(res, offs, ALL, flags=flags, threads=8)
+        got, _ = shb.hash_batch(res, offs, ALL, flags=flags)
+        for k, a in enumerate(ALL):
+            assert (got[k] == want[k]).all(), (a, flags)
+
+
+def test_strip_and_emit(shb, oracle):
+    # whitespace strip (seqhasher.go:246) incl. records that become empty, plus the normalised sequences
+    recs = [b"AC TG ", b"AC\tTG", b"AC\nTG", b"actg", b" \t\n", b"", b"A" * 5000 + b" " + b"c" * 4000, b"\x0b\x0cN\r"]
+    rng = np.random.default_rng(9)
+    for _ in range(300):
+        n = int(rng.integers(0, 9000))
+        r = rng.choice(np.frombuffer(b"ACGTacgtN \t\n\r", dtype=np.uint8), size=n)
+        recs.append(r.tobytes())
+    res, offs = csr_from_records(recs)
+    for flags in (2, 3):
+        want, wl = oracle.batch(res, offs, ALL, flags=flags, threads=8)
+        got, gl, (nres, noffs) = shb.hash_batch(res, offs, ALL, flags=flags, emit=True)
+        assert (gl == wl).all()
+        for k, a in enumerate(ALL):
+            assert (got[k] == want[k]).all(), (a, flags)
+        for i in (0, 1, 2, 3, 4, 5, 6, 7, 50, 307):
+            assert nres[noffs[i]:noffs[i + 1]].tobytes() == oracle.normalise(recs[i], flags)
+    outs, lens = shb.hash_batch(*csr_from_records(recs[:6]), ["sha1"], flags=3)
+    assert _hex(outs[0], lens) == [G.ACTG["sha1"]] * 4 + ["", ""]
+
+
+def test_duplicate_algos_and_empty_batch(shb):
+    res, offs = csr_from_records([b"ACTG", b"TGCA"])
+    outs, lens = shb.hash_batch(res, offs, ["sha1", "md5", "sha1"], flags=0)
+    assert (outs[0] == outs[2]).all() and _hex(outs[1], lens)[1] == "5c15f97a88433c48f8bf76745d9da437"
+    outs, lens = shb.hash_batch(np.zeros(0, np.uint8), np.zeros(1, np.int64), ["sha1"], flags=3)
+    assert outs[0].shape == (0, 20)
+
+
+def test_synth_generator_matches_numpy_twin(shb):
+    import torch
+    from synth import synth_bytes
+    total = 100003
+    t = torch.empty(total + 16, dtype=torch.uint8, device="cuda")
+    shb.synth_fill(t.data_ptr(), total, seed=0xC2, lower_permille=50, n_permille=1,
+                   stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (t[:total].cpu().numpy() == synth_bytes(total, 0xC2, 50, 1)).all()
+
+
+def test_device_resident_path_fixed_length_reads(shb, oracle):
+    # C2 / C3 shapes (250 bp and 150 bp fixed-length reads) at a size the oracle finishes in seconds
+    import torch
+    from synth import synth_bytes
+    st = torch.cuda.current_stream().cuda_stream
+    for L, algos in ((250, ["sha1", "xxh3"]), (150, ["xxhash", "xxh3", "murmur3"])):
+        n = 200_000
+        total = n * L
+        d_res = torch.empty(total + 16, dtype=torch.uint8, device="cuda")
+        shb.synth_fill(d_res.data_ptr(), total, seed=0xC2, lower_permille=30, stream=st)
+        d_offs = torch.arange(0, n + 1, dtype=torch.int64, device="cuda") * L
+        outs = [torch.empty(n * shb.DIGEST_SIZES[shb.algo_id(a)], dtype=torch.uint8, device="cuda") for a in algos]
+        shb.hash_device(d_res.data_ptr(), d_offs.data_ptr(), n, total, algos, shb.FLAG_UPPER,
+                        [o.data_ptr() for o in outs], stream=st)
+        torch.cuda.synchronize()
+        res = synth_bytes(total, 0xC2, 30)
+        want, _ = oracle.batch(res, d_offs.cpu().numpy(), algos, flags=1, threads=8, accel=True)
+        for k, a in enumerate(algos):
+            assert (outs[k].cpu().numpy().reshape(n, -1) == want[k]).all(), (L, a)
