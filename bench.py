@@ -219,10 +219,10 @@ def main():
     roof_sha1 = {"bound": "int", "achieved": sha1_ach / 1e12, "peak": (int_peak or theo) / 1e12, "unit": "T lane-instr/s",
                  "frac": sha1_ach / (int_peak or theo), "peak_source": int_src, "frac_of_theoretical_issue": sha1_ach / theo,
                  "work": f"{SHA1_INSTR_PER_BLOCK} int ops x {blocks_per_rec} blocks x {n} records per launch",
-                 "hbm_gbps": alg_bytes_sha1 / (ms_sha1 * 1e-3) / 1e9, "traffic": None, "kernel": "hash_direct_kernel<sha1>"}
+                 "hbm_gbps": alg_bytes_sha1 / (ms_sha1 * 1e-3) / 1e9, "traffic": None, "kernel": "hash_tile_kernel<sha1>"}
     xxh3_gbps = alg_bytes_xxh3 / (ms_xxh3 * 1e-3) / 1e9
     roof_xxh3 = {"bound": "hbm", "achieved": xxh3_gbps, "peak": hbm_peak, "unit": "GB/s", "frac": xxh3_gbps / hbm_peak,
-                 "peak_source": peak_src, "traffic": None, "kernel": "hash_direct_kernel<xxh3>",
+                 "peak_source": peak_src, "traffic": None, "kernel": "hash_tile_kernel<xxh3>",
                  "bytes": f"{alg_bytes_xxh3} algorithmic bytes per launch (residues + 8 B offsets + 8 B digest per record)"}
 
     # ---- e2e through the C ABI with host buffers ----

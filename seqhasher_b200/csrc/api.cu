@@ -77,18 +77,29 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
     }
     if (norm_res) *norm_res = res;
     if (norm_offs) *norm_offs = offs;
-    for (int k = 0; k < n_algos; k++) {
-        // identical algo requested twice: compute once, copy the slot (the reference recomputes)
-        int prev = -1;
-        for (int j = 0; j < k; j++)
-            if (algos[j] == algos[k]) { prev = j; break; }
-        if (prev >= 0) {
-            CU(cudaMemcpyAsync(d_digests[k], d_digests[prev], n * shb::digest_size(algos[k]),
-                               cudaMemcpyDeviceToDevice, st));
-            continue;
-        }
-        CU(shb::launch_hash_direct(algos[k], fused_upper, res, offs, n, d_digests[k], st));
+    // Path choice.  Short records (mean <= 640 B): shared-memory tiles of 128 records, sized so that at
+    // least two CTAs fit per SM; the HBM-bound hashes requested together are fused into one launch so the
+    // residues are read once.  Longer records: one thread per record straight from global memory.
+    uint8_t *slot_of[SHB_N_ALGOS] = {};
+    uint32_t want = 0;
+    for (int k = 0; k < n_algos; k++)
+        if (!slot_of[algos[k]]) { slot_of[algos[k]] = d_digests[k]; want |= 1u << algos[k]; }
+    const size_t mean = n ? total_bytes / n : 0;
+    const size_t tile_need = (mean * 128 * 5 / 4 + 1024 + 1023) / 1024 * 1024;
+    if (n && tile_need <= 100 * 1024) {
+        const uint32_t cap = (uint32_t)(tile_need < 8192 ? 8192 : tile_need);
+        const uint32_t fast = want & shb::tile_fast_mask();
+        if (fast) CU(shb::launch_hash_tile(fast, fused_upper, res, offs, n, slot_of, cap, st));
+        for (int a = 0; a < SHB_N_ALGOS; a++)
+            if ((want & ~fast) >> a & 1u) CU(shb::launch_hash_tile(1u << a, fused_upper, res, offs, n, slot_of, cap, st));
+    } else {
+        for (int a = 0; a < SHB_N_ALGOS; a++)
+            if (want >> a & 1u) CU(shb::launch_hash_direct(a, fused_upper, res, offs, n, slot_of[a], st));
     }
+    // an algorithm requested twice ("--hash sha1,sha1"): computed once, the slot is copied
+    for (int k = 0; k < n_algos; k++)
+        if (slot_of[algos[k]] != d_digests[k])
+            CU(cudaMemcpyAsync(d_digests[k], slot_of[algos[k]], n * shb::digest_size(algos[k]), cudaMemcpyDeviceToDevice, st));
     return SHB_OK;
 }
 

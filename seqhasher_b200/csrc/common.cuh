@@ -5,8 +5,8 @@
 // seqhasher.go:241).  Two readers exist:
 //   GlobalReader<UPPER>  — straight from HBM/L2/L1 (direct path; upper-casing fused in the load,
 //                          seqhasher.go:249-251)
-//   SmemReader           — from a shared-memory tile that was staged by bulk async copy and
-//                          upper-cased in place once per tile
+//   SmemReader<UPPER>    — from a shared-memory tile that was staged by a TMA bulk copy; upper-
+//                          casing either fused in the load (one hash) or done in place beforehand
 // Both return words by funnel-shifting two aligned 32-bit loads, so no unaligned access is ever
 // issued; both may read (never use) up to 7 bytes past the record end, which the buffers pad.
 #pragma once
@@ -82,6 +82,7 @@ struct GlobalReader {
     __device__ __forceinline__ uint32_t u8(uint32_t off) const { return u32x(off) & 0xffu; }
 };
 
+template <bool UPPER>
 struct SmemReader {
     const uint32_t *w;
     uint32_t bo, sh;
@@ -94,13 +95,15 @@ struct SmemReader {
     __device__ __forceinline__ uint32_t u32(uint32_t off) const
     {
         const uint32_t *q = w + (off >> 2);
-        return __funnelshift_r(q[0], q[1], sh);
+        uint32_t v = __funnelshift_r(q[0], q[1], sh);
+        return UPPER ? upper4(v) : v;
     }
     __device__ __forceinline__ uint32_t u32x(uint32_t off) const
     {
         uint32_t a = off + bo;
         const uint32_t *q = w + (a >> 2);
-        return __funnelshift_r(q[0], q[1], (a & 3) * 8);
+        uint32_t v = __funnelshift_r(q[0], q[1], (a & 3) * 8);
+        return UPPER ? upper4(v) : v;
     }
     __device__ __forceinline__ uint64_t u64(uint32_t off) const { return mk64(u32(off), u32(off + 4)); }
     __device__ __forceinline__ uint64_t u64x(uint32_t off) const
@@ -109,7 +112,9 @@ struct SmemReader {
         const uint32_t *q = w + (a >> 2);
         uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
         uint32_t s = (a & 3) * 8;
-        return mk64(__funnelshift_r(w0, w1, s), __funnelshift_r(w1, w2, s));
+        uint32_t lo = __funnelshift_r(w0, w1, s), hi = __funnelshift_r(w1, w2, s);
+        if (UPPER) { lo = upper4(lo); hi = upper4(hi); }
+        return mk64(lo, hi);
     }
     __device__ __forceinline__ uint32_t u8(uint32_t off) const { return u32x(off) & 0xffu; }
 };
@@ -132,6 +137,36 @@ __device__ __forceinline__ void store_be64(uint8_t *out, uint64_t v)
 {
     uint2 t = make_uint2(bswap32((uint32_t)(v >> 32)), bswap32((uint32_t)v));
     *reinterpret_cast<uint2 *>(out) = t;
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+/sm_100a PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bytes: multiple of 16; src and dst 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 }  // namespace shb

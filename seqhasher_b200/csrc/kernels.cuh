@@ -27,6 +27,14 @@ inline size_t norm_blocks(size_t total_bytes) { return total_bytes / NORM_BLK + 
 cudaError_t launch_hash_direct(int algo, bool upper, const uint8_t *res, const int64_t *offs, size_t n,
                                uint8_t *out, cudaStream_t st);
 
+// Tile path (tile.cu): CTA-staged shared-memory tiles of 128 records, one thread per record.  `mask` has
+// bit a set for every algorithm to compute; more than one bit is allowed only inside tile_fast_mask()
+// (the HBM-bound hashes, fused so the residues are read once).  outs[a] = digest array of algo a.
+// cap = shared-memory tile budget in bytes; tiles that exceed it read global memory directly.
+cudaError_t launch_hash_tile(uint32_t mask, bool upper, const uint8_t *res, const int64_t *offs, size_t n,
+                             uint8_t *const *outs, uint32_t cap, cudaStream_t st);
+uint32_t tile_fast_mask();
+
 // Normalise pre-pass (seqhasher.go:246-251 materialised): whitespace strip (if strip) + upper-casing
 // (if upper) of the whole CSR batch into out_res / out_offs (n+1) / out_len (n, may be null).
 // block_counts: norm_blocks() uint32; block_prefix: norm_blocks()+1 int64.

@@ -1,0 +1,161 @@
+// tile.cu — the short-record path: one CTA stages a contiguous run of records (a "tile") from the
+// CSR residue buffer into shared memory with one 1-D TMA bulk copy (cp.async.bulk + mbarrier), then
+// every thread hashes one record out of shared memory.
+//
+// Why: 150-250-byte records at arbitrary byte offsets waste most of every 32-byte sector when each
+// thread reads its own record from global memory; the tile is read from HBM exactly once, fully
+// coalesced, and the per-thread unaligned reads hit shared memory instead.  Several CTAs are resident
+// per SM so one CTA's TMA load overlaps its neighbours' hashing.
+//
+// A kernel instance handles a compile-time SET of algorithms (MASK): with more than one, the tile is
+// upper-cased in place once and every requested hash reads the same staged bytes (the reference
+// re-reads the record per hash, seqhasher.go:255-259).  Tiles that do not fit the shared-memory
+// budget fall back, per CTA, to direct global reads, so any input is still handled.
+#include "hash_all.cuh"
+
+namespace shb {
+
+struct OutPtrs {
+    uint8_t *p[N_ALGOS];
+};
+
+template <uint32_t MASK, int ALGO, class R>
+__device__ __forceinline__ void hash_if(const R &r, uint32_t len, size_t i, const OutPtrs &out, uint32_t rmask)
+{
+    if ((MASK >> ALGO) & 1u) {
+        if ((rmask >> ALGO) & 1u) {
+            uint8_t *o = out.p[ALGO] + i * digest_size(ALGO);
+            if (len == 0) zero_digest<ALGO>(o);   // empty-sequence rule, seqhasher.go:292-295
+            else hash_one<ALGO>(r, len, o);
+        }
+    }
+}
+
+template <uint32_t MASK, class R>
+__device__ __forceinline__ void hash_set(const R &r, uint32_t len, size_t i, const OutPtrs &out, uint32_t rmask)
+{
+    hash_if<MASK, A_SHA1>(r, len, i, out, rmask);
+    hash_if<MASK, A_SHA3>(r, len, i, out, rmask);
+    hash_if<MASK, A_MD5>(r, len, i, out, rmask);
+    hash_if<MASK, A_XXHASH>(r, len, i, out, rmask);
+    hash_if<MASK, A_XXH3>(r, len, i, out, rmask);
+    hash_if<MASK, A_CITYHASH>(r, len, i, out, rmask);
+    hash_if<MASK, A_MURMUR3>(r, len, i, out, rmask);
+    hash_if<MASK, A_NTHASH>(r, len, i, out, rmask);
+    hash_if<MASK, A_BLAKE3>(r, len, i, out, rmask);
+    hash_if<MASK, A_K12>(r, len, i, out, rmask);
+    hash_if<MASK, A_RAPIDHASH>(r, len, i, out, rmask);
+    hash_if<MASK, A_RAPIDHASH32>(r, len, i, out, rmask);
+}
+
+constexpr uint32_t TMA_CHUNK = 32768;   // one bulk copy moves at most this many bytes
+
+template <uint32_t MASK, bool UPPER>
+__global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restrict__ res,
+                                                        const int64_t *__restrict__ offs, size_t n, OutPtrs out,
+                                                        uint32_t rmask, uint32_t cap)
+{
+    constexpr bool MULTI = (MASK & (MASK - 1)) != 0;
+    extern __shared__ __align__(128) uint8_t tile[];   // cap + 32 bytes
+    __shared__ uint64_t mbar;
+
+    const size_t r0 = (size_t)blockIdx.x * blockDim.x;
+    const size_t r1 = (r0 + blockDim.x < n) ? r0 + blockDim.x : n;
+    const size_t i = r0 + threadIdx.x;
+    // every thread reads the tile bounds (same address: one broadcast transaction) and its own record
+    const int64_t t_start = offs[r0], t_end = offs[r1];
+    int64_t s = 0, e = 0;
+    if (i < n) { s = offs[i]; e = offs[i + 1]; }
+    const uint32_t len = (uint32_t)(e - s);
+    const int64_t a0 = t_start & ~(int64_t)15;            // residue base is 16-byte aligned
+    const int64_t span = (t_end - a0 + 15) & ~(int64_t)15;
+
+    if (span <= (int64_t)cap) {
+        const uint32_t bytes = (uint32_t)span;
+        if (bytes) {
+            if (threadIdx.x == 0) mbar_init(&mbar, 1);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&mbar, bytes);
+                for (uint32_t o = 0; o < bytes; o += TMA_CHUNK)
+                    tma_bulk_g2s(tile + o, res + a0 + o, (bytes - o < TMA_CHUNK) ? bytes - o : TMA_CHUNK, &mbar);
+            }
+            mbar_wait(&mbar, 0);
+            if (MULTI && UPPER) {   // seqhasher.go:249-251 once per tile, then every hash reads it
+                uint4 *t4 = reinterpret_cast<uint4 *>(tile);
+                for (uint32_t k = threadIdx.x; k < (bytes >> 4); k += blockDim.x) {
+                    uint4 v = t4[k];
+                    v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w);
+                    t4[k] = v;
+                }
+                __syncthreads();
+            }
+        }
+        if (i < n) {
+            SmemReader<UPPER && !MULTI> r(tile, (uint32_t)(s - a0));
+            hash_set<MASK>(r, len, i, out, rmask);
+        }
+    } else if (i < n) {
+        GlobalReader<UPPER> r(res, s);
+        hash_set<MASK>(r, len, i, out, rmask);
+    }
+}
+
+constexpr uint32_t bit(int a) { return 1u << a; }
+constexpr uint32_t FAST_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_CITYHASH) | bit(A_MURMUR3) | bit(A_NTHASH) |
+                               bit(A_RAPIDHASH) | bit(A_RAPIDHASH32);
+constexpr uint32_t C3_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_MURMUR3);
+
+template <uint32_t MASK>
+static cudaError_t launch_tile_t(bool upper, const uint8_t *res, const int64_t *offs, size_t n, const OutPtrs &out,
+                                 uint32_t rmask, uint32_t cap, cudaStream_t st)
+{
+    const unsigned threads = 128;
+    const size_t blocks = (n + threads - 1) / threads;
+    const size_t smem = (size_t)cap + 32;
+    cudaError_t e;
+    if (upper) {
+        e = cudaFuncSetAttribute(hash_tile_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hash_tile_kernel<MASK, true><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap);
+    } else {
+        e = cudaFuncSetAttribute(hash_tile_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        hash_tile_kernel<MASK, false><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap);
+    }
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// Hash every algorithm of `mask` (bit a = algo a) over the batch; outs[a] is the digest array of algo a.
+cudaError_t launch_hash_tile(uint32_t mask, bool upper, const uint8_t *res, const int64_t *offs, size_t n,
+                             uint8_t *const *outs, uint32_t cap, cudaStream_t st)
+{
+    if (n == 0 || mask == 0) return cudaSuccess;
+    OutPtrs out;
+    for (int a = 0; a < N_ALGOS; a++) out.p[a] = outs[a];
+    if ((mask & (mask - 1)) == 0) {
+        switch (mask) {
+        case bit(A_SHA1): return launch_tile_t<bit(A_SHA1)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_SHA3): return launch_tile_t<bit(A_SHA3)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_MD5): return launch_tile_t<bit(A_MD5)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_XXHASH): return launch_tile_t<bit(A_XXHASH)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_XXH3): return launch_tile_t<bit(A_XXH3)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_CITYHASH): return launch_tile_t<bit(A_CITYHASH)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_MURMUR3): return launch_tile_t<bit(A_MURMUR3)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_NTHASH): return launch_tile_t<bit(A_NTHASH)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_BLAKE3): return launch_tile_t<bit(A_BLAKE3)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_K12): return launch_tile_t<bit(A_K12)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_RAPIDHASH): return launch_tile_t<bit(A_RAPIDHASH)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_RAPIDHASH32): return launch_tile_t<bit(A_RAPIDHASH32)>(upper, res, offs, n, out, mask, cap, st);
+        }
+        return cudaErrorInvalidValue;
+    }
+    if (mask == C3_MASK) return launch_tile_t<C3_MASK>(upper, res, offs, n, out, mask, cap, st);
+    if ((mask & ~FAST_MASK) == 0) return launch_tile_t<FAST_MASK>(upper, res, offs, n, out, mask, cap, st);
+    return cudaErrorInvalidValue;   // callers split crypto algorithms into single-bit launches
+}
+
+uint32_t tile_fast_mask() { return FAST_MASK; }
+
+}  // namespace shb

@@ -131,3 +131,34 @@ def test_device_resident_path_fixed_length_reads(shb, oracle):
         want, _ = oracle.batch(res, d_offs.cpu().numpy(), algos, flags=1, threads=8, accel=True)
         for k, a in enumerate(algos):
             assert (outs[k].cpu().numpy().reshape(n, -1) == want[k]).all(), (L, a)
+
+
+def test_tile_path_ragged_tiles_and_fallback(shb, oracle):
+    # mean length is short (shared-memory tile path) but some 128-record tiles hold a 60 kB record and do
+    # not fit the tile budget: those CTAs must fall back to direct global reads; also empty records, a
+    # tile made only of empty records, and a last partial tile
+    rng = np.random.default_rng(77)
+    lens = rng.integers(0, 260, size=128 * 40 + 17)
+    lens[300] = 60_000
+    lens[2000] = 75_001
+    lens[128 * 5: 128 * 6] = 0
+    res, offs = csr_from_lengths(lens, seed=0x7153, lower_permille=400, n_permille=30)
+    for flags in (0, 1):
+        want, _ = oracle.batch(res, offs, ALL, flags=flags, threads=8)
+        got, _ = shb.hash_batch(res, offs, ALL, flags=flags)
+        for k, a in enumerate(ALL):
+            bad = np.nonzero((got[k] != want[k]).any(axis=1))[0]
+            assert bad.size == 0, f"{a} flags={flags}: mismatch at records {bad[:8]} lens {lens[bad[:8]]}"
+
+
+@pytest.mark.parametrize("L", [1, 31, 150, 250, 251, 640])
+def test_tile_path_fixed_lengths_fused_sets(shb, oracle, L):
+    n = 128 * 30 + 5
+    res, offs = csr_from_lengths([L] * n, seed=L, lower_permille=100, n_permille=5)
+    sets = [["xxhash", "xxh3", "murmur3"], ["nthash", "cityhash"], ["rapidhash", "rapidhash32", "xxh3", "sha1", "md5"],
+            ["blake3", "k12", "sha3"]]
+    for algos in sets:
+        want, _ = oracle.batch(res, offs, algos, flags=1, threads=8)
+        got, _ = shb.hash_batch(res, offs, algos, flags=1)
+        for k, a in enumerate(algos):
+            assert (got[k] == want[k]).all(), (L, a)
