@@ -127,8 +127,12 @@ int shb_synth_fill(int device, uint8_t *d_residues, size_t total_bytes, uint64_t
 
 /* Register-only integer throughput probes: kind 0 LOP3, 1 IADD3, 2 SHF, 3 IMAD, 4 PRMT,
  * 5 the SHA-1 instruction mix (LOP3:IADD3:SHF:PRMT = 208:165:224:16),
- * 6 LOP3+IMAD interleaved 1:1.  Returns lane-instructions per second, or <0. */
+ * 6 LOP3+IMAD interleaved 1:1;
+ * 16+v: the SHA-1 compression loop on register data with pipe-balancing variant v (hash_md.cuh);
+ * 7 = 16.  Returns lane-instructions per second (613 per compression), or <0. */
 double shb_probe_int_peak(int device, int kind, int iters);
+/* XOR checksum of the final states of the last SHA-1 probe (every variant must give the same value). */
+unsigned shb_probe_last_checksum(void);
 
 #ifdef __cplusplus
 }

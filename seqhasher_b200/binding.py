@@ -27,7 +27,7 @@ EXPORTS = [
     "shb_digest_size", "shb_batch_create", "shb_batch_create_on", "shb_batch_destroy", "shb_batch_residues",
     "shb_batch_offsets", "shb_submit", "shb_wait", "shb_digests", "shb_out_lengths", "shb_out_offsets",
     "shb_out_residues", "shb_scratch_bytes", "shb_hash_device", "shb_launch_count", "shb_synth_fill",
-    "shb_probe_int_peak",
+    "shb_probe_int_peak", "shb_probe_last_checksum",
 ]
 
 
@@ -74,6 +74,7 @@ def lib() -> ctypes.CDLL:
     L.shb_synth_fill.argtypes = [c.c_int, c.c_void_p, c.c_size_t, c.c_uint64, c.c_uint, c.c_uint, c.c_void_p]
     L.shb_synth_fill.restype = c.c_int
     L.shb_probe_int_peak.argtypes = [c.c_int, c.c_int, c.c_int]; L.shb_probe_int_peak.restype = c.c_double
+    L.shb_probe_last_checksum.argtypes = []; L.shb_probe_last_checksum.restype = c.c_uint
     _lib = L
     return L
 
@@ -222,3 +223,7 @@ def launch_count() -> int:
 
 def probe_int_peak(kind: int, iters: int = 2000, device: int = 0) -> float:
     return lib().shb_probe_int_peak(device, kind, iters)
+
+
+def probe_last_checksum() -> int:
+    return lib().shb_probe_last_checksum()

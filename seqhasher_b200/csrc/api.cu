@@ -347,6 +347,9 @@ int shb_synth_fill(int device, uint8_t *d_residues, size_t total_bytes, uint64_t
     return SHB_OK;
 }
 
+static uint32_t g_probe_checksum = 0;
+unsigned shb_probe_last_checksum(void) { return g_probe_checksum; }
+
 double shb_probe_int_peak(int device, int kind, int iters)
 {
     if (g_ndev == 0 && shb_init(0, 0) < 0) return -1.0;
@@ -359,6 +362,7 @@ double shb_probe_int_peak(int device, int kind, int iters)
     double lane_instr = 0;
     double best = -1.0;
     for (int rep = 0; rep < 4; rep++) {   // rep 0 warms up
+        cudaMemsetAsync(sink, 0, 64, 0);
         cudaEventRecord(e0, 0);
         if (shb::launch_probe(kind, iters, sink, &lane_instr, 0) != cudaSuccess) { best = -1.0; break; }
         cudaEventRecord(e1, 0);
@@ -368,6 +372,9 @@ double shb_probe_int_peak(int device, int kind, int iters)
         double rate = lane_instr / (ms * 1e-3);
         if (rep > 0 && rate > best) best = rate;
     }
+    uint32_t host_sink[2] = {0, 0};
+    cudaMemcpy(host_sink, sink, sizeof host_sink, cudaMemcpyDeviceToHost);
+    g_probe_checksum = host_sink[1];
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);

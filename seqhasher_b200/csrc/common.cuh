@@ -46,12 +46,21 @@ struct GlobalReader {
     const uint32_t *w;   // aligned-down word pointer of the record start
     uint32_t bo;         // start & 3
     uint32_t sh;         // bo * 8
+    uint32_t besel;      // PRMT selector: bytes bo+3, bo+2, bo+1, bo of a word pair = big-endian word
     __device__ __forceinline__ GlobalReader(const uint8_t *base, int64_t start)
     {
         uintptr_t a = (uintptr_t)base + (uintptr_t)start;
         w = (const uint32_t *)(a & ~(uintptr_t)3);
         bo = (uint32_t)(a & 3);
         sh = bo * 8;
+        besel = 0x0123u + bo * 0x1111u;
+    }
+    // big-endian 32-bit word at byte offset `off` (multiple of 4): alignment and byte swap in one PRMT
+    __device__ __forceinline__ uint32_t u32be(uint32_t off) const
+    {
+        const uint32_t *q = w + (off >> 2);
+        uint32_t v = __byte_perm(__ldg(q), __ldg(q + 1), besel);
+        return UPPER ? upper4(v) : v;
     }
     // 32-bit LE word at byte offset `off` (multiple of 4) of the record
     __device__ __forceinline__ uint32_t u32(uint32_t off) const
@@ -85,12 +94,19 @@ struct GlobalReader {
 template <bool UPPER>
 struct SmemReader {
     const uint32_t *w;
-    uint32_t bo, sh;
+    uint32_t bo, sh, besel;
     __device__ __forceinline__ SmemReader(const uint8_t *tile, uint32_t start)
     {
         w = (const uint32_t *)(tile + (start & ~3u));
         bo = start & 3u;
         sh = bo * 8;
+        besel = 0x0123u + bo * 0x1111u;
+    }
+    __device__ __forceinline__ uint32_t u32be(uint32_t off) const
+    {
+        const uint32_t *q = w + (off >> 2);
+        uint32_t v = __byte_perm(q[0], q[1], besel);
+        return UPPER ? upper4(v) : v;
     }
     __device__ __forceinline__ uint32_t u32(uint32_t off) const
     {

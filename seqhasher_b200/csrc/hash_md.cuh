@@ -10,7 +10,25 @@
 
 namespace shb {
 
-__device__ __forceinline__ void sha1_compress(uint32_t (&h)[5], uint32_t (&w)[16])
+// Pipe balancing.  SHA-1 is bound by the ALU pipe (LOP3/SHF/IADD3/PRMT: 64 lanes/clk/SM on sm_100)
+// while the FMA pipe (IMAD: another 64 lanes/clk/SM) idles.  A rotate by a constant is
+// hi32(x * 2^k) + lo32(x * 2^k): one IMAD.WIDE plus one IMAD on the FMA pipe instead of one SHF on the
+// ALU pipe.  The multipliers come from kernel parameters (values the compiler cannot see), otherwise
+// ptxas folds the products back into shifts.  VARIANT bits choose what moves to the FMA pipe:
+//   1: rol(b,30)   2: the schedule's rol(.,1)   4: rol(a,5) as two separate addends   8: W[t]+K
+struct PipeConsts {
+    uint32_t one, p1, p5, p30;   // 1, 2, 32, 1<<30
+};
+__host__ __device__ inline PipeConsts pipe_consts() { return PipeConsts{1u, 2u, 32u, 1u << 30}; }
+
+__device__ __forceinline__ uint32_t fma_rol(uint32_t x, uint32_t pow2, uint32_t one)
+{
+    uint64_t p = (uint64_t)x * (uint64_t)pow2;
+    return (uint32_t)(p >> 32) * one + (uint32_t)p;
+}
+
+template <int VARIANT>
+__device__ __forceinline__ void sha1_compress_v(uint32_t (&h)[5], uint32_t (&w)[16], const PipeConsts &pc)
 {
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
 #pragma unroll
@@ -19,7 +37,8 @@ __device__ __forceinline__ void sha1_compress(uint32_t (&h)[5], uint32_t (&w)[16
         if (t < 16) {
             wt = w[t];
         } else {
-            wt = rotl32(w[(t - 3) & 15] ^ w[(t - 8) & 15] ^ w[(t - 14) & 15] ^ w[t & 15], 1);
+            uint32_t x = w[(t - 3) & 15] ^ w[(t - 8) & 15] ^ w[(t - 14) & 15] ^ w[t & 15];
+            wt = (VARIANT & 2) ? fma_rol(x, pc.p1, pc.one) : rotl32(x, 1);
             w[t & 15] = wt;
         }
         uint32_t f, k;
@@ -27,10 +46,31 @@ __device__ __forceinline__ void sha1_compress(uint32_t (&h)[5], uint32_t (&w)[16
         else if (t < 40) { f = b ^ c ^ d; k = 0x6ED9EBA1u; }
         else if (t < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8F1BBCDCu; }
         else { f = b ^ c ^ d; k = 0xCA62C1D6u; }
-        uint32_t tmp = rotl32(a, 5) + f + e + k + wt;
-        e = d; d = c; c = rotl32(b, 30); b = a; a = tmp;
+        const uint32_t kw = (VARIANT & 8) ? wt * pc.one + k : wt + k;
+        uint32_t tmp;
+        if (VARIANT & 4) {
+            uint64_t p = (uint64_t)a * (uint64_t)pc.p5;
+            tmp = ((uint32_t)p + (uint32_t)(p >> 32) + f) + (e + kw);
+        } else {
+            tmp = rotl32(a, 5) + f + e + kw;
+        }
+        e = d; d = c;
+        c = (VARIANT & 1) ? fma_rol(b, pc.p30, pc.one) : rotl32(b, 30);
+        b = a; a = tmp;
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
+}
+
+// The multiplier 1 as a value ptxas cannot see (a __constant__ may be rewritten by the host, so loads
+// of it are never folded): x * c_one + y is an IMAD on the FMA pipe instead of an IADD3 on the ALU pipe.
+static __constant__ uint32_t c_one = 1u;
+
+// Production form = variant 8 (measured fastest on B200, tools/probe_sha1_variants.py): only the
+// W[t]+K adds are forced onto the FMA pipe, which also makes ptxas emit the remaining two-input adds as
+// IMAD.IADD; IMAD.WIDE-based rotates are slower than SHF and stay off.
+__device__ __forceinline__ void sha1_compress(uint32_t (&h)[5], uint32_t (&w)[16])
+{
+    sha1_compress_v<8>(h, w, PipeConsts{c_one, 2u, 32u, 1u << 30});
 }
 
 // out: 20 bytes, 4-byte aligned
@@ -44,7 +84,7 @@ __device__ __forceinline__ void sha1_record(const R &r, uint32_t len, uint8_t *o
         uint32_t w[16];
         if (base + 64 <= len) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) w[i] = bswap32(r.u32(base + 4 * i));
+            for (int i = 0; i < 16; i++) w[i] = r.u32be(base + 4 * i);   // align + byte-swap in one PRMT
         } else {
 #pragma unroll
             for (int i = 0; i < 16; i++) w[i] = bswap32(padded_u32(r, base + 4 * i, len, 0x80u));

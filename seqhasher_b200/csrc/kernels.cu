@@ -330,18 +330,29 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, uint32_t *sink)
     if (acc == 0x12345u) sink[0] = acc;   // practically never true; keeps the chains alive
 }
 
-// kind 7: the real SHA-1 compression on register data (613 fused ops per call by the survey's count)
-__global__ void __launch_bounds__(128) probe_sha1_kernel(int iters, uint32_t *sink)
+// kinds 16..31: the real SHA-1 compression on register data, pipe-balancing variant = kind - 16
+// (613 fused ops per call by the survey's count); kind 7 = variant 0
+template <int VARIANT>
+__global__ void __launch_bounds__(128) probe_sha1_kernel(int iters, uint32_t *sink, PipeConsts pc)
 {
     uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) w[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
     for (int it = 0; it < iters; it++) {
-        sha1_compress(h, w);
+        sha1_compress_v<VARIANT>(h, w, pc);
         w[0] ^= h[0];
     }
-    if ((h[0] ^ h[1] ^ h[2] ^ h[3] ^ h[4]) == 0x12345u) sink[0] = h[0];
+    // digest of the chain; the host cross-checks every variant against variant 0
+    uint32_t x = h[0] ^ h[1] ^ h[2] ^ h[3] ^ h[4];
+    for (int d = 16; d; d >>= 1) x ^= __shfl_xor_sync(0xffffffffu, x, d);
+    if ((threadIdx.x & 31) == 0) atomicXor(sink + 1, x);
+}
+
+template <int V>
+static void launch_probe_sha1(int iters, uint32_t *sink, cudaStream_t st)
+{
+    probe_sha1_kernel<V><<<148 * 16, 128, 0, st>>>(iters, sink, pipe_consts());
 }
 
 cudaError_t launch_probe(int kind, int iters, uint32_t *sink, double *lane_instr, cudaStream_t st)
@@ -355,11 +366,26 @@ cudaError_t launch_probe(int kind, int iters, uint32_t *sink, double *lane_instr
     case 4: probe_kernel<4><<<blocks, 256, 0, st>>>(iters, sink); break;
     case 5: probe_kernel<5><<<blocks, 256, 0, st>>>(iters, sink); break;
     case 6: probe_kernel<6><<<blocks, 256, 0, st>>>(iters, sink); break;
-    case 7: probe_sha1_kernel<<<148 * 16, 128, 0, st>>>(iters, sink); break;
+    case 7: case 16: launch_probe_sha1<0>(iters, sink, st); break;
+    case 17: launch_probe_sha1<1>(iters, sink, st); break;
+    case 18: launch_probe_sha1<2>(iters, sink, st); break;
+    case 19: launch_probe_sha1<3>(iters, sink, st); break;
+    case 20: launch_probe_sha1<4>(iters, sink, st); break;
+    case 21: launch_probe_sha1<5>(iters, sink, st); break;
+    case 22: launch_probe_sha1<6>(iters, sink, st); break;
+    case 23: launch_probe_sha1<7>(iters, sink, st); break;
+    case 24: launch_probe_sha1<8>(iters, sink, st); break;
+    case 25: launch_probe_sha1<9>(iters, sink, st); break;
+    case 26: launch_probe_sha1<10>(iters, sink, st); break;
+    case 27: launch_probe_sha1<11>(iters, sink, st); break;
+    case 28: launch_probe_sha1<12>(iters, sink, st); break;
+    case 29: launch_probe_sha1<13>(iters, sink, st); break;
+    case 30: launch_probe_sha1<14>(iters, sink, st); break;
+    case 31: launch_probe_sha1<15>(iters, sink, st); break;
     default: return cudaErrorInvalidValue;
     }
     g_launches++;
-    if (kind == 7) *lane_instr = 148.0 * 16 * 128 * (double)iters * 613.0;
+    if (kind == 7 || kind >= 16) *lane_instr = 148.0 * 16 * 128 * (double)iters * 613.0;
     else *lane_instr = (double)blocks * 256.0 * (double)iters * 64.0 * 8.0 * (kind == 1 ? 1.0 : 1.0);
     return cudaGetLastError();
 }
