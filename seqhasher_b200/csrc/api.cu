@@ -39,7 +39,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // scratch layout of the normalise pre-pass inside one allocation
 struct ScratchLayout {
-    size_t res_off, offs_off, counts_off, prefix_off, total;
+    size_t res_off, offs_off, counts_off, prefix_off, b3_off, total;
     ScratchLayout(size_t total_bytes, size_t n)
     {
         const size_t nb = shb::norm_blocks(total_bytes);
@@ -47,7 +47,8 @@ struct ScratchLayout {
         offs_off = align_up(total_bytes + 32, 256);
         counts_off = offs_off + align_up((n + 1) * sizeof(int64_t), 256);
         prefix_off = counts_off + align_up(nb * sizeof(uint32_t), 256);
-        total = prefix_off + align_up((nb + 1) * sizeof(int64_t), 256);
+        b3_off = prefix_off + align_up((nb + 1) * sizeof(int64_t), 256);   // BLAKE3 long path: counts, bases, CVs
+        total = b3_off + shb::b3_long_scratch_bytes(total_bytes, n);
     }
 };
 
@@ -60,8 +61,18 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
     const uint8_t *res = d_res;
     const int64_t *offs = d_offs;
     bool fused_upper = upper;
-    if (strip || emit) {
-        if (!d_scratch) return fail(SHB_ERR_BAD_ARG, "SHB_FLAG_STRIP/EMIT_SEQ need a scratch buffer");
+    // Path choice.  Short records (mean <= 640 B): shared-memory tiles of 128 records, sized so that at
+    // least two CTAs fit per SM; the HBM-bound hashes requested together are fused into one launch so the
+    // residues are read once, and the whitespace strip is fused into the tile pass.  Longer records: one
+    // thread per record straight from global memory, or the long-record kernels (mean >= 2 KiB).
+    const size_t mean = n ? total_bytes / n : 0;
+    const size_t tile_need = (mean * 128 * 5 / 4 + 1024 + 1023) / 1024 * 1024;
+    const bool tile_mode = n && tile_need <= 100 * 1024;
+    const bool prepass = emit || (strip && !tile_mode);   // materialise the normalised batch first
+    uint8_t *fused_strip_scratch = nullptr;
+    int64_t *fused_out_len = nullptr;
+    if ((strip || emit) && !d_scratch) return fail(SHB_ERR_BAD_ARG, "SHB_FLAG_STRIP/EMIT_SEQ need a scratch buffer");
+    if (prepass) {
         ScratchLayout L(total_bytes, n);
         uint8_t *base = static_cast<uint8_t *>(d_scratch);
         uint8_t *o_res = base + L.res_off;
@@ -72,29 +83,52 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         res = o_res;
         offs = o_offs;
         fused_upper = false;   // already applied while compacting
+    } else if (strip) {
+        fused_strip_scratch = static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).res_off;
+        fused_out_len = d_out_len;
     } else if (d_out_len) {
         CU(shb::launch_lengths(d_offs, n, d_out_len, st));
     }
     if (norm_res) *norm_res = res;
     if (norm_offs) *norm_offs = offs;
-    // Path choice.  Short records (mean <= 640 B): shared-memory tiles of 128 records, sized so that at
-    // least two CTAs fit per SM; the HBM-bound hashes requested together are fused into one launch so the
-    // residues are read once.  Longer records: one thread per record straight from global memory.
     uint8_t *slot_of[SHB_N_ALGOS] = {};
     uint32_t want = 0;
     for (int k = 0; k < n_algos; k++)
         if (!slot_of[algos[k]]) { slot_of[algos[k]] = d_digests[k]; want |= 1u << algos[k]; }
-    const size_t mean = n ? total_bytes / n : 0;
-    const size_t tile_need = (mean * 128 * 5 / 4 + 1024 + 1023) / 1024 * 1024;
-    if (n && tile_need <= 100 * 1024) {
+    if (tile_mode) {
         const uint32_t cap = (uint32_t)(tile_need < 8192 ? 8192 : tile_need);
         const uint32_t fast = want & shb::tile_fast_mask();
-        if (fast) CU(shb::launch_hash_tile(fast, fused_upper, res, offs, n, slot_of, cap, st));
+        if (fast) {
+            CU(shb::launch_hash_tile(fast, fused_upper, res, offs, n, slot_of, cap, fused_strip_scratch, fused_out_len, st));
+            fused_out_len = nullptr;   // lengths are written by the first launch only
+        }
         for (int a = 0; a < SHB_N_ALGOS; a++)
-            if ((want & ~fast) >> a & 1u) CU(shb::launch_hash_tile(1u << a, fused_upper, res, offs, n, slot_of, cap, st));
+            if ((want & ~fast) >> a & 1u) {
+                CU(shb::launch_hash_tile(1u << a, fused_upper, res, offs, n, slot_of, cap, fused_strip_scratch, fused_out_len, st));
+                fused_out_len = nullptr;
+            }
+        if (fused_out_len)   // strip requested with no algorithm at all: lengths still have to be produced
+            CU(shb::launch_normalise(d_res, d_offs, n, total_bytes, true, false,
+                                     reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).counts_off),
+                                     reinterpret_cast<int64_t *>(static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).prefix_off),
+                                     static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).res_off,
+                                     reinterpret_cast<int64_t *>(static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).offs_off),
+                                     d_out_len, st));
     } else {
-        for (int a = 0; a < SHB_N_ALGOS; a++)
-            if (want >> a & 1u) CU(shb::launch_hash_direct(a, fused_upper, res, offs, n, slot_of[a], st));
+        // mean >= 2 KiB: the hashes with parallelism inside a record leave the thread-per-record path
+        const bool long_mode = n && mean >= 2048;
+        for (int a = 0; a < SHB_N_ALGOS; a++) {
+            if (!(want >> a & 1u)) continue;
+            if (long_mode && a == SHB_NTHASH) {
+                CU(shb::launch_nthash_long(fused_upper, res, offs, n, slot_of[a], st));
+            } else if (long_mode && a == SHB_BLAKE3 && d_scratch) {
+                ScratchLayout L(total_bytes, n);
+                CU(shb::launch_blake3_long(fused_upper, res, offs, n, total_bytes, slot_of[a],
+                                           static_cast<uint8_t *>(d_scratch) + L.b3_off, st));
+            } else {
+                CU(shb::launch_hash_direct(a, fused_upper, res, offs, n, slot_of[a], st));
+            }
+        }
     }
     // an algorithm requested twice ("--hash sha1,sha1"): computed once, the slot is copied
     for (int k = 0; k < n_algos; k++)
@@ -257,7 +291,9 @@ int shb_submit(shb_batch *b, size_t n, const int *algos, int n_algos, unsigned f
         b->dig_cap = need;
     }
     const bool norm = flags & (SHB_FLAG_STRIP | SHB_FLAG_EMIT_SEQ);
-    if (norm) {
+    bool wants_b3_long = false;
+    for (int k = 0; k < n_algos; k++) wants_b3_long |= (algos[k] == SHB_BLAKE3 && n && total / n >= 2048);
+    if (norm || wants_b3_long) {
         const size_t sneed = ScratchLayout(b->max_bytes, b->max_records).total;
         if (sneed > b->scratch_cap) {
             CU(cudaStreamSynchronize(b->stream));

@@ -41,8 +41,11 @@ __device__ __forceinline__ uint32_t upper4(uint32_t x)
 // reference whitespace set for ASCII input (bytes.Fields fast path, seqhasher.go:246)
 __device__ __forceinline__ bool is_ws(uint32_t c) { return c == 0x20u || (c - 9u) <= 4u; }
 
-template <bool UPPER>
+// NC = true reads through the non-coherent path (ld.global.nc); NC = false is for buffers written earlier
+// in the same kernel (the strip scratch).
+template <bool UPPER, bool NC = true>
 struct GlobalReader {
+    static __device__ __forceinline__ uint32_t ld(const uint32_t *p) { return NC ? __ldg(p) : *p; }
     const uint32_t *w;   // aligned-down word pointer of the record start
     uint32_t bo;         // start & 3
     uint32_t sh;         // bo * 8
@@ -59,14 +62,14 @@ struct GlobalReader {
     __device__ __forceinline__ uint32_t u32be(uint32_t off) const
     {
         const uint32_t *q = w + (off >> 2);
-        uint32_t v = __byte_perm(__ldg(q), __ldg(q + 1), besel);
+        uint32_t v = __byte_perm(ld(q), ld(q + 1), besel);
         return UPPER ? upper4(v) : v;
     }
     // 32-bit LE word at byte offset `off` (multiple of 4) of the record
     __device__ __forceinline__ uint32_t u32(uint32_t off) const
     {
         const uint32_t *q = w + (off >> 2);
-        uint32_t v = __funnelshift_r(__ldg(q), __ldg(q + 1), sh);
+        uint32_t v = __funnelshift_r(ld(q), ld(q + 1), sh);
         return UPPER ? upper4(v) : v;
     }
     // 32-bit LE word at ANY byte offset
@@ -74,7 +77,7 @@ struct GlobalReader {
     {
         uint32_t a = off + bo;
         const uint32_t *q = w + (a >> 2);
-        uint32_t v = __funnelshift_r(__ldg(q), __ldg(q + 1), (a & 3) * 8);
+        uint32_t v = __funnelshift_r(ld(q), ld(q + 1), (a & 3) * 8);
         return UPPER ? upper4(v) : v;
     }
     __device__ __forceinline__ uint64_t u64(uint32_t off) const { return mk64(u32(off), u32(off + 4)); }
@@ -82,7 +85,7 @@ struct GlobalReader {
     {
         uint32_t a = off + bo;
         const uint32_t *q = w + (a >> 2);
-        uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+        uint32_t w0 = ld(q), w1 = ld(q + 1), w2 = ld(q + 2);
         uint32_t s = (a & 3) * 8;
         uint32_t lo = __funnelshift_r(w0, w1, s), hi = __funnelshift_r(w1, w2, s);
         if (UPPER) { lo = upper4(lo); hi = upper4(hi); }

@@ -145,6 +145,14 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t *__res
     if (hi == nb && lo <= nb) prefix[nb] = run;   // several threads may write the same total
 }
 
+// exclusive scan of n uint32 counts into n+1 int64 prefixes (used by the BLAKE3 long path too)
+cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, cudaStream_t st)
+{
+    scan_blocks_kernel<<<1, 1024, 0, st>>>(counts, n, prefix);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 template <bool STRIP, bool UPPER>
 __global__ void __launch_bounds__(256) compact_kernel(const uint8_t *__restrict__ res, size_t total,
                                                       const int64_t *__restrict__ offs, size_t n,

@@ -31,9 +31,20 @@ cudaError_t launch_hash_direct(int algo, bool upper, const uint8_t *res, const i
 // bit a set for every algorithm to compute; more than one bit is allowed only inside tile_fast_mask()
 // (the HBM-bound hashes, fused so the residues are read once).  outs[a] = digest array of algo a.
 // cap = shared-memory tile budget in bytes; tiles that exceed it read global memory directly.
+// strip_scratch != nullptr fuses the whitespace strip into the tile pass (needs total_bytes + 32 bytes of
+// scratch for the rare oversize tile); out_len (may be null) then receives the post-strip lengths.
 cudaError_t launch_hash_tile(uint32_t mask, bool upper, const uint8_t *res, const int64_t *offs, size_t n,
-                             uint8_t *const *outs, uint32_t cap, cudaStream_t st);
+                             uint8_t *const *outs, uint32_t cap, uint8_t *strip_scratch, int64_t *out_len,
+                             cudaStream_t st);
 uint32_t tile_fast_mask();
+
+// Long-record path (long.cu): ntHash warp-per-record; BLAKE3 thread-per-chunk over the flattened chunk
+// list + thread-per-record tree merge (scratch: b3_long_scratch_bytes()).
+cudaError_t launch_nthash_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, uint8_t *out,
+                               cudaStream_t st);
+size_t b3_long_scratch_bytes(size_t total_bytes, size_t n);
+cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
+                               uint8_t *out, void *scratch, cudaStream_t st);
 
 // Normalise pre-pass (seqhasher.go:246-251 materialised): whitespace strip (if strip) + upper-casing
 // (if upper) of the whole CSR batch into out_res / out_offs (n+1) / out_len (n, may be null).

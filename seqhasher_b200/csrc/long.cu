@@ -1,0 +1,280 @@
+// long.cu — the long-record path (10-50 kb nanopore-like reads, BASELINE config C4): the hashes that
+// have parallelism INSIDE one record get it here instead of one serial thread per record.
+//
+//   ntHash  : warp per record.  The forward hash is a pure XOR of rotated seeds (nthash.go ntf64;
+//             seqhasher.go:320-327), so lanes take 16-byte units with coalesced 128-bit loads, fold each
+//             unit with pre-rotated seed look-ups and XOR-reduce across the warp.
+//   BLAKE3  : thread per 1024-byte CHUNK over the flattened chunk list of the whole batch (every lane
+//             always has a full chunk of work, whatever the record lengths), chaining values to a scratch
+//             array; then one thread per record merges its CVs up the binary tree (n-1 parents against
+//             16n chunk compressions).  Replaces blake3.Sum256 (seqhasher.go:328-330).
+//
+// Upper-casing (seqhasher.go:249-251) is fused into the loads of both.
+#include "hash_all.cuh"
+
+namespace shb {
+
+// ------------------------------------------------------------------------------------------- ntHash
+
+// seed LUTs pre-rotated by 3,2,1,0: a 4-byte word folds as rol(h,4) ^ L3[b0] ^ L2[b1] ^ L1[b2] ^ L0[b3]
+struct NtLut {
+    uint64_t rot[4][256];
+};
+
+__device__ __forceinline__ void nt_fill_lut(NtLut *lut)
+{
+    for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) {
+        const uint64_t s = nt_seed(c);
+#pragma unroll
+        for (int k = 0; k < 4; k++) lut->rot[k][c] = k ? rotl64(s, k) : s;
+    }
+}
+
+// fold 4 bytes (memory order b0..b3) into h
+__device__ __forceinline__ uint64_t nt_fold4(uint64_t h, uint32_t w, const NtLut *lut)
+{
+    return rotl64(h, 4) ^ lut->rot[3][w & 0xffu] ^ lut->rot[2][(w >> 8) & 0xffu] ^ lut->rot[1][(w >> 16) & 0xffu] ^
+           lut->rot[0][w >> 24];
+}
+
+__device__ __forceinline__ uint64_t rotl64v(uint64_t x, uint32_t r)   // r in 0..63, run-time
+{
+    r &= 63u;
+    return r ? (x << r) | (x >> (64 - r)) : x;
+}
+
+// byte k of the result is 0xff where position (pos + k) lies inside [0, len), else 0
+__device__ __forceinline__ uint32_t valid_mask4(int64_t pos, int64_t len)
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (pos + k >= 0 && pos + k < len) m |= 0xffu << (8 * k);
+    return m;
+}
+
+template <bool UPPER>
+__global__ void __launch_bounds__(256) nthash_warp_kernel(const uint8_t *__restrict__ res,
+                                                          const int64_t *__restrict__ offs, size_t n,
+                                                          uint8_t *__restrict__ out)
+{
+    __shared__ NtLut lut;
+    nt_fill_lut(&lut);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const int64_t s = offs[i], e = offs[i + 1];
+        const int64_t len = e - s;
+        uint8_t *o = out + i * 8;
+        if (len == 0) {   // empty-sequence rule, seqhasher.go:292-295
+            if (lane == 0) *reinterpret_cast<uint2 *>(o) = make_uint2(0u, 0u);
+            continue;
+        }
+        // 16-byte units of the aligned window that covers the record
+        const int64_t a0 = s & ~(int64_t)15;
+        const int64_t nunits = (e - a0 + 15) >> 4;
+        uint64_t acc = 0;
+        for (int64_t u = lane; u < nunits; u += 32) {
+            const int64_t pos = a0 + 16 * u - s;   // record position of the unit's first byte (may be < 0)
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(res + a0) + u);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const bool interior = pos >= 0 && pos + 16 <= len;
+            if (!interior) {   // bytes outside the record contribute nothing: map them to 0 (seed 0)
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[k] &= valid_mask4(pos + 4 * k, len);
+            }
+            uint64_t t = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) t = nt_fold4(t, UPPER ? upper4(w[k]) : w[k], &lut);
+            // t = XOR_j rol(seed[b_j], 15 - j); position pos+j carries rotation (len-1-pos-j) mod 64
+            acc ^= rotl64v(t, (uint32_t)((len - 16 - pos) & 63));
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) store_be64(o, acc);
+    }
+}
+
+cudaError_t launch_nthash_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, uint8_t *out,
+                               cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n + 7) / 8;   // 8 warps per CTA
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    if (upper) nthash_warp_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(res, offs, n, out);
+    else nthash_warp_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(res, offs, n, out);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------- BLAKE3
+
+// chunks of record i = max(1, ceil(len/1024)); written as uint32 counts for the shared scan kernel
+__global__ void b3_count_chunks_kernel(const int64_t *__restrict__ offs, size_t n, uint32_t *__restrict__ counts)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t len = offs[i + 1] - offs[i];
+        counts[i] = len ? (uint32_t)((len + 1023) >> 10) : 0u;   // empty records own no chunk
+    }
+}
+
+// 16 message words of the 64-byte block at p (any alignment): five aligned 128-bit loads + funnel shifts
+template <bool UPPER>
+__device__ __forceinline__ void load_block16(const uint8_t *p, uint32_t (&w)[16])
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>((uintptr_t)p & ~(uintptr_t)15);
+    const uint32_t m = (uint32_t)((uintptr_t)p & 15u);
+    uint32_t u[20];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint4 v = __ldg(q + k);
+        u[4 * k] = v.x; u[4 * k + 1] = v.y; u[4 * k + 2] = v.z; u[4 * k + 3] = v.w;
+    }
+    if (m) {
+        uint4 v = __ldg(q + 4);
+        u[16] = v.x; u[17] = v.y; u[18] = v.z; u[19] = v.w;
+    } else {
+        u[16] = u[17] = u[18] = u[19] = 0;
+    }
+    const uint32_t sh = (m & 3u) * 8u;
+    switch (m >> 2) {
+    case 0:
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = __funnelshift_r(u[i], u[i + 1], sh);
+        break;
+    case 1:
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = __funnelshift_r(u[i + 1], u[i + 2], sh);
+        break;
+    case 2:
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = __funnelshift_r(u[i + 2], u[i + 3], sh);
+        break;
+    default:
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = __funnelshift_r(u[i + 3], u[i + 4], sh);
+        break;
+    }
+    if (UPPER) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = upper4(w[i]);
+    }
+}
+
+// One thread per chunk of the flattened chunk list.  chunk_base[i] = number of chunks before record i
+// (exclusive scan of the counts, chunk_base[n] = total).  Single-chunk records are finished here (ROOT);
+// for the others the chunk CV goes to cvs[global chunk id].
+template <bool UPPER>
+__global__ void __launch_bounds__(128) b3_chunks_kernel(const uint8_t *__restrict__ res,
+                                                        const int64_t *__restrict__ offs, size_t n,
+                                                        const int64_t *__restrict__ chunk_base,
+                                                        uint32_t *__restrict__ cvs, uint8_t *__restrict__ out)
+{
+    const int64_t total = chunk_base[n];
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    // record that owns chunk g: last i with chunk_base[i] <= g (records with zero chunks are skipped)
+    size_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const size_t mid = (lo + hi) >> 1;
+        if (chunk_base[mid] <= g) lo = mid; else hi = mid;
+    }
+    const size_t i = lo;
+    const int64_t s = offs[i], len = offs[i + 1] - s;
+    const uint32_t c = (uint32_t)(g - chunk_base[i]);
+    const uint32_t nchunks = (uint32_t)((len + 1023) >> 10);
+    const uint32_t clen = (c + 1 < nchunks) ? 1024u : (uint32_t)(len - ((int64_t)c << 10));
+    const uint32_t root = (nchunks == 1) ? (uint32_t)B3_ROOT : 0u;
+    uint32_t cv[8];
+    if (clen == 1024u) {
+        const uint8_t *p = res + s + ((int64_t)c << 10);
+        b3_set_iv(cv);
+#pragma unroll 1
+        for (uint32_t b = 0; b < 16; b++) {
+            uint32_t m[16];
+            load_block16<UPPER>(p + 64 * b, m);
+            const uint32_t flags = (b == 0 ? (uint32_t)B3_CHUNK_START : 0u) | (b == 15 ? ((uint32_t)B3_CHUNK_END | root) : 0u);
+            b3_compress(cv, m, c, 0u, 64u, flags);
+        }
+    } else {
+        GlobalReader<UPPER> r(res, s);
+        b3_chunk_cv(r, c << 10, clen, c, root, cv);
+    }
+    uint32_t *dst = root ? reinterpret_cast<uint32_t *>(out + i * 32) : cvs + g * 8;
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    *reinterpret_cast<uint4 *>(dst + 4) = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+// One thread per record with >= 2 chunks: lazy binary-counter merge of its chunk CVs (same tree as
+// blake3_record in hash_blake3.cuh); empty records get the all-zero slot.
+__global__ void __launch_bounds__(128) b3_merge_kernel(const int64_t *__restrict__ offs, size_t n,
+                                                       const int64_t *__restrict__ chunk_base,
+                                                       const uint32_t *__restrict__ cvs, uint8_t *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t base = chunk_base[i];
+    const uint32_t nchunks = (uint32_t)(chunk_base[i + 1] - base);
+    uint32_t *o = reinterpret_cast<uint32_t *>(out + i * 32);
+    if (nchunks == 0) {   // empty-sequence rule
+        *reinterpret_cast<uint4 *>(o) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(o + 4) = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    if (nchunks == 1) return;   // finished by b3_chunks_kernel
+    uint32_t stack[22][8];
+    int depth = 0;
+    uint32_t cv[8];
+    for (uint32_t c = 0; c < nchunks; c++) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(cvs + (base + c) * 8));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(cvs + (base + c) * 8 + 4));
+        cv[0] = a.x; cv[1] = a.y; cv[2] = a.z; cv[3] = a.w; cv[4] = b.x; cv[5] = b.y; cv[6] = b.z; cv[7] = b.w;
+        if (c + 1 < nchunks) {
+            for (uint32_t tot = c + 1; (tot & 1u) == 0; tot >>= 1) b3_parent(stack[--depth], cv, 0u);
+#pragma unroll
+            for (int k = 0; k < 8; k++) stack[depth][k] = cv[k];
+            depth++;
+        }
+    }
+    while (depth > 0) {
+        depth--;
+        b3_parent(stack[depth], cv, depth == 0 ? (uint32_t)B3_ROOT : 0u);
+    }
+    *reinterpret_cast<uint4 *>(o) = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    *reinterpret_cast<uint4 *>(o + 4) = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+size_t b3_long_scratch_bytes(size_t total_bytes, size_t n)
+{
+    const size_t max_chunks = total_bytes / 1024 + n + 1;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    return up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)) + up(max_chunks * 32);
+}
+
+cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, cudaStream_t st);   // kernels.cu
+
+cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
+                               uint8_t *out, void *scratch, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    uint8_t *base = static_cast<uint8_t *>(scratch);
+    uint32_t *counts = reinterpret_cast<uint32_t *>(base);
+    int64_t *chunk_base = reinterpret_cast<int64_t *>(base + up(n * sizeof(uint32_t)));
+    uint32_t *cvs = reinterpret_cast<uint32_t *>(base + up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)));
+    b3_count_chunks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(offs, n, counts);
+    g_launches++;
+    cudaError_t e = scan_counts(counts, n, chunk_base, st);
+    if (e != cudaSuccess) return e;
+    const size_t max_chunks = total_bytes / 1024 + n + 1;   // upper bound of chunk_base[n]; the kernel re-checks
+    const unsigned blocks = (unsigned)((max_chunks + 127) / 128);
+    if (upper) b3_chunks_kernel<true><<<blocks, 128, 0, st>>>(res, offs, n, chunk_base, cvs, out);
+    else b3_chunks_kernel<false><<<blocks, 128, 0, st>>>(res, offs, n, chunk_base, cvs, out);
+    b3_merge_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(offs, n, chunk_base, cvs, out);
+    g_launches += 2;
+    return cudaGetLastError();
+}
+
+}  // namespace shb

@@ -50,10 +50,47 @@ __device__ __forceinline__ void hash_set(const R &r, uint32_t len, size_t i, con
 
 constexpr uint32_t TMA_CHUNK = 32768;   // one bulk copy moves at most this many bytes
 
+// ---- whitespace strip fused into the tile pass (seqhasher.go:246) ----
+// non-zero iff some byte of w is < 0x21 (every ASCII whitespace byte is): exact as an ANY test
+__device__ __forceinline__ uint32_t has_byte_below_0x21(uint32_t w) { return (w - 0x21212121u) & ~w & 0x80808080u; }
+
+// compact the record [start, start+len) of the tile in place; returns the new length
+__device__ __forceinline__ uint32_t strip_in_smem(uint8_t *tile, uint32_t start, uint32_t len)
+{
+    // cheap test first: aligned words covering the record (neighbouring bytes can only cause a false alarm)
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + (start & ~3u));
+    const uint32_t nw = ((start & 3u) + len + 3u) >> 2;
+    uint32_t f = 0;
+    for (uint32_t k = 0; k < nw; k++) f |= has_byte_below_0x21(wp[k]);
+    if (!f) return len;
+    uint32_t j = start;
+    for (uint32_t i = start; i < start + len; i++) {
+        const uint8_t c = tile[i];
+        if (!is_ws(c)) tile[j++] = c;
+    }
+    return j - start;
+}
+
+// same for a record that is not staged: compacted copy into the scratch buffer at the same offset
+__device__ __forceinline__ uint32_t strip_to_scratch(const uint8_t *__restrict__ res, uint8_t *__restrict__ scratch,
+                                                     int64_t s, uint32_t len)
+{
+    uint32_t j = 0;
+    for (uint32_t i = 0; i < len; i++) {
+        const uint8_t c = res[s + i];
+        if (!is_ws(c)) scratch[s + j++] = c;
+    }
+    return j;
+}
+
+// strip_scratch != nullptr turns the whitespace strip on: the staged tile is tested once (cooperatively)
+// for any byte < 0x21; only if one exists do the threads compact their own records in shared memory.
+// out_len (may be null) receives the post-strip length of every record.
 template <uint32_t MASK, bool UPPER>
 __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restrict__ res,
                                                         const int64_t *__restrict__ offs, size_t n, OutPtrs out,
-                                                        uint32_t rmask, uint32_t cap)
+                                                        uint32_t rmask, uint32_t cap, uint8_t *strip_scratch,
+                                                        int64_t *__restrict__ out_len)
 {
     constexpr bool MULTI = (MASK & (MASK - 1)) != 0;
     extern __shared__ __align__(128) uint8_t tile[];   // cap + 32 bytes
@@ -66,7 +103,8 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     const int64_t t_start = offs[r0], t_end = offs[r1];
     int64_t s = 0, e = 0;
     if (i < n) { s = offs[i]; e = offs[i + 1]; }
-    const uint32_t len = (uint32_t)(e - s);
+    uint32_t len = (uint32_t)(e - s);
+    const bool strip = strip_scratch != nullptr;
     const int64_t a0 = t_start & ~(int64_t)15;            // residue base is 16-byte aligned
     const int64_t span = (t_end - a0 + 15) & ~(int64_t)15;
 
@@ -81,23 +119,39 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
                     tma_bulk_g2s(tile + o, res + a0 + o, (bytes - o < TMA_CHUNK) ? bytes - o : TMA_CHUNK, &mbar);
             }
             mbar_wait(&mbar, 0);
-            if (MULTI && UPPER) {   // seqhasher.go:249-251 once per tile, then every hash reads it
+            if ((MULTI && UPPER) || strip) {
+                // one cooperative pass over the tile: upper-case in place when several hashes will read
+                // it (seqhasher.go:249-251), and look for whitespace candidates (seqhasher.go:246)
                 uint4 *t4 = reinterpret_cast<uint4 *>(tile);
+                uint32_t f = 0;
                 for (uint32_t k = threadIdx.x; k < (bytes >> 4); k += blockDim.x) {
                     uint4 v = t4[k];
-                    v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w);
-                    t4[k] = v;
+                    if (strip) f |= has_byte_below_0x21(v.x) | has_byte_below_0x21(v.y) | has_byte_below_0x21(v.z) |
+                                    has_byte_below_0x21(v.w);
+                    if (MULTI && UPPER) {
+                        v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w);
+                        t4[k] = v;
+                    }
                 }
-                __syncthreads();
+                const int any_ws = __syncthreads_or(strip && f != 0);
+                if (any_ws && i < n && len) len = strip_in_smem(tile, (uint32_t)(s - a0), len);
             }
         }
         if (i < n) {
+            if (strip && out_len) out_len[i] = len;
             SmemReader<UPPER && !MULTI> r(tile, (uint32_t)(s - a0));
             hash_set<MASK>(r, len, i, out, rmask);
         }
     } else if (i < n) {
-        GlobalReader<UPPER> r(res, s);
-        hash_set<MASK>(r, len, i, out, rmask);
+        if (strip) {
+            len = strip_to_scratch(res, strip_scratch, s, len);
+            if (out_len) out_len[i] = len;
+            GlobalReader<UPPER, false> r(strip_scratch, s);   // written by this thread just above
+            hash_set<MASK>(r, len, i, out, rmask);
+        } else {
+            GlobalReader<UPPER> r(res, s);
+            hash_set<MASK>(r, len, i, out, rmask);
+        }
     }
 }
 
@@ -108,7 +162,7 @@ constexpr uint32_t C3_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_MURMUR3);
 
 template <uint32_t MASK>
 static cudaError_t launch_tile_t(bool upper, const uint8_t *res, const int64_t *offs, size_t n, const OutPtrs &out,
-                                 uint32_t rmask, uint32_t cap, cudaStream_t st)
+                                 uint32_t rmask, uint32_t cap, uint8_t *strip_scratch, int64_t *out_len, cudaStream_t st)
 {
     const unsigned threads = 128;
     const size_t blocks = (n + threads - 1) / threads;
@@ -117,11 +171,11 @@ static cudaError_t launch_tile_t(bool upper, const uint8_t *res, const int64_t *
     if (upper) {
         e = cudaFuncSetAttribute(hash_tile_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hash_tile_kernel<MASK, true><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap);
+        hash_tile_kernel<MASK, true><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap, strip_scratch, out_len);
     } else {
         e = cudaFuncSetAttribute(hash_tile_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        hash_tile_kernel<MASK, false><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap);
+        hash_tile_kernel<MASK, false><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap, strip_scratch, out_len);
     }
     g_launches++;
     return cudaGetLastError();
@@ -129,30 +183,31 @@ static cudaError_t launch_tile_t(bool upper, const uint8_t *res, const int64_t *
 
 // Hash every algorithm of `mask` (bit a = algo a) over the batch; outs[a] is the digest array of algo a.
 cudaError_t launch_hash_tile(uint32_t mask, bool upper, const uint8_t *res, const int64_t *offs, size_t n,
-                             uint8_t *const *outs, uint32_t cap, cudaStream_t st)
+                             uint8_t *const *outs, uint32_t cap, uint8_t *strip_scratch, int64_t *out_len,
+                             cudaStream_t st)
 {
     if (n == 0 || mask == 0) return cudaSuccess;
     OutPtrs out;
     for (int a = 0; a < N_ALGOS; a++) out.p[a] = outs[a];
     if ((mask & (mask - 1)) == 0) {
         switch (mask) {
-        case bit(A_SHA1): return launch_tile_t<bit(A_SHA1)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_SHA3): return launch_tile_t<bit(A_SHA3)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_MD5): return launch_tile_t<bit(A_MD5)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_XXHASH): return launch_tile_t<bit(A_XXHASH)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_XXH3): return launch_tile_t<bit(A_XXH3)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_CITYHASH): return launch_tile_t<bit(A_CITYHASH)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_MURMUR3): return launch_tile_t<bit(A_MURMUR3)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_NTHASH): return launch_tile_t<bit(A_NTHASH)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_BLAKE3): return launch_tile_t<bit(A_BLAKE3)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_K12): return launch_tile_t<bit(A_K12)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_RAPIDHASH): return launch_tile_t<bit(A_RAPIDHASH)>(upper, res, offs, n, out, mask, cap, st);
-        case bit(A_RAPIDHASH32): return launch_tile_t<bit(A_RAPIDHASH32)>(upper, res, offs, n, out, mask, cap, st);
+        case bit(A_SHA1): return launch_tile_t<bit(A_SHA1)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_SHA3): return launch_tile_t<bit(A_SHA3)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_MD5): return launch_tile_t<bit(A_MD5)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_XXHASH): return launch_tile_t<bit(A_XXHASH)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_XXH3): return launch_tile_t<bit(A_XXH3)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_CITYHASH): return launch_tile_t<bit(A_CITYHASH)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_MURMUR3): return launch_tile_t<bit(A_MURMUR3)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_NTHASH): return launch_tile_t<bit(A_NTHASH)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_BLAKE3): return launch_tile_t<bit(A_BLAKE3)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_K12): return launch_tile_t<bit(A_K12)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_RAPIDHASH): return launch_tile_t<bit(A_RAPIDHASH)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+        case bit(A_RAPIDHASH32): return launch_tile_t<bit(A_RAPIDHASH32)>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
         }
         return cudaErrorInvalidValue;
     }
-    if (mask == C3_MASK) return launch_tile_t<C3_MASK>(upper, res, offs, n, out, mask, cap, st);
-    if ((mask & ~FAST_MASK) == 0) return launch_tile_t<FAST_MASK>(upper, res, offs, n, out, mask, cap, st);
+    if (mask == C3_MASK) return launch_tile_t<C3_MASK>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
+    if ((mask & ~FAST_MASK) == 0) return launch_tile_t<FAST_MASK>(upper, res, offs, n, out, mask, cap, strip_scratch, out_len, st);
     return cudaErrorInvalidValue;   // callers split crypto algorithms into single-bit launches
 }
 

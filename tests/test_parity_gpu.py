@@ -162,3 +162,60 @@ def test_tile_path_fixed_lengths_fused_sets(shb, oracle, L):
         got, _ = shb.hash_batch(res, offs, algos, flags=1)
         for k, a in enumerate(algos):
             assert (got[k] == want[k]).all(), (L, a)
+
+
+def test_long_record_path(shb, oracle):
+    # mean length >= 2 KiB switches ntHash to warp-per-record and BLAKE3 to chunk-parallel + tree merge
+    rng = np.random.default_rng(4)
+    lens = [0, 1, 1023, 1024, 1025, 2047, 2048, 2049, 3072, 3073, 4096, 5000, 31744, 32768, 32769, 33000, 65536, 65537,
+            70000, 100000, 131072, 0, 64, 7 * 1024 + 1] + list(rng.integers(2000, 60000, size=300))
+    res, offs = csr_from_lengths(lens, seed=0xC4, lower_permille=100, n_permille=10)
+    algos = ["blake3", "nthash", "xxh3", "sha1", "k12"]
+    for flags in (0, 1, 3):
+        want, wl = oracle.batch(res, offs, algos, flags=flags, threads=8)
+        got, gl = shb.hash_batch(res, offs, algos, flags=flags)
+        assert (gl == wl).all()
+        for k, a in enumerate(algos):
+            bad = np.nonzero((got[k] != want[k]).any(axis=1))[0]
+            assert bad.size == 0, f"{a} flags={flags}: mismatch at lengths {[lens[i] for i in bad[:8]]}"
+    # arbitrary bytes (ntHash's non-ACGT -> 0 rule, every alignment) on the long path
+    lens2 = rng.integers(1500, 9000, size=400)
+    offs2 = np.zeros(len(lens2) + 1, dtype=np.int64)
+    np.cumsum(lens2, out=offs2[1:])
+    res2 = rng.integers(0, 256, size=int(offs2[-1]), dtype=np.uint8)
+    want, _ = oracle.batch(res2, offs2, ["nthash", "blake3"], flags=1, threads=8)
+    got, _ = shb.hash_batch(res2, offs2, ["nthash", "blake3"], flags=1)
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+
+
+def test_fused_strip_in_tile_path(shb, oracle):
+    # short records (tile path): strip fused into the staged tile; tiles without whitespace take the fast
+    # path, tiles with whitespace compact in shared memory, an oversize tile compacts through scratch
+    rng = np.random.default_rng(12)
+    recs = []
+    for k in range(128 * 12 + 3):
+        n = int(rng.integers(0, 300))
+        alphabet = b"ACGTacgtN" if (k // 128) % 2 == 0 else b"ACGTacgtN \t\n\r\x0b\x0c"
+        recs.append(rng.choice(np.frombuffer(alphabet, dtype=np.uint8), size=n).tobytes())
+    recs[700] = (b"AC GT\n" * 12000)          # 72 kB record in a short-mean batch: oversize tile
+    recs[5] = b" \t \n"                        # strips to empty
+    res, offs = csr_from_records(recs)
+    assert int(offs[-1]) // len(recs) <= 640
+    for flags in (2, 3):
+        want, wl = oracle.batch(res, offs, ALL, flags=flags, threads=8)
+        got, gl = shb.hash_batch(res, offs, ALL, flags=flags)
+        assert (gl == wl).all()
+        for k, a in enumerate(ALL):
+            bad = np.nonzero((got[k] != want[k]).any(axis=1))[0]
+            assert bad.size == 0, f"{a} flags={flags}: mismatch at records {bad[:8]}"
+
+
+def test_hash_sharded_single_process(shb, oracle):
+    # the in-process multi-device driver (one shb_batch per device); on a 1-GPU box this is one shard
+    import torch
+    from seqhasher_b200.shard import hash_sharded
+    n_gpus = min(torch.cuda.device_count(), 2)
+    res, offs = csr_from_lengths(np.random.default_rng(3).integers(0, 600, size=5000), seed=21, lower_permille=50)
+    want, wl = oracle.batch(res, offs, ["sha1", "xxh3"], flags=3, threads=4)
+    got, gl = hash_sharded(res, offs, ["sha1", "xxh3"], 3, n_gpus)
+    assert (gl == wl).all() and (got[0] == want[0]).all() and (got[1] == want[1]).all()

@@ -28,9 +28,7 @@ def run(name, n, lens, algos, flags, seed, lower, n_perm, steps, hbm_peak):
     res = torch.empty(total + 16, dtype=torch.uint8, device=dev)
     B.synth_fill(res.data_ptr(), total, seed, lower, n_perm, stream=st)
     outs = [torch.empty(n * B.DIGEST_SIZES[B.algo_id(a)], dtype=torch.uint8, device=dev) for a in algos]
-    scratch = None
-    if flags & B.FLAG_STRIP:
-        scratch = torch.empty(B.scratch_bytes(total, n), dtype=torch.uint8, device=dev)
+    scratch = torch.empty(B.scratch_bytes(total, n), dtype=torch.uint8, device=dev)   # strip pre-pass / BLAKE3 CVs
     call = lambda: B.hash_device(res.data_ptr(), offs.data_ptr(), n, total, algos, flags, [o.data_ptr() for o in outs],
                                  d_scratch=scratch.data_ptr() if scratch is not None else None, stream=st)
     for _ in range(3):
@@ -75,6 +73,10 @@ def main():
     if "C4" in only:
         out.append(run("C4: 10-50 kb nanopore-like reads, blake3+nthash, case-sensitive", int(1_000_000 * a.scale),
                        (10_000, 50_000), ["blake3", "nthash"], 0, 0xC4, 0, 1, a.steps, hbm))
+    if "C4split" in only:
+        for algo in ["nthash", "blake3", "xxh3", "sha1", "k12", "xxhash", "murmur3", "cityhash", "rapidhash", "md5", "sha3"]:
+            out.append(run(f"C4 shape (x{a.scale}), {algo} alone", int(1_000_000 * a.scale), (10_000, 50_000), [algo], 0,
+                           0xC4, 0, 1, a.steps, hbm))
     if "C5" in only:
         out.append(run("C5: 30-3000 bp variable reads, all 12, strip+upper", int(5_000_000 * a.scale), (30, 3000),
                        B.ALGO_NAMES, B.FLAG_UPPER | B.FLAG_STRIP, 0xC5, 50, 1, a.steps, hbm))
