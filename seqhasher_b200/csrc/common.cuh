@@ -94,35 +94,42 @@ struct GlobalReader {
     __device__ __forceinline__ uint32_t u8(uint32_t off) const { return u32x(off) & 0xffu; }
 };
 
-template <bool UPPER>
+// DETECT = true also ORs a "some byte < 0x21" test of every word handed out into `wsf` (bit 7 of a byte
+// set => a whitespace candidate was read): the speculative whitespace detection of the fused strip.
+template <bool UPPER, bool DETECT = false>
 struct SmemReader {
     const uint32_t *w;
     uint32_t bo, sh, besel;
+    mutable uint32_t wsf;
     __device__ __forceinline__ SmemReader(const uint8_t *tile, uint32_t start)
     {
         w = (const uint32_t *)(tile + (start & ~3u));
         bo = start & 3u;
         sh = bo * 8;
         besel = 0x0123u + bo * 0x1111u;
+        wsf = 0;
     }
+    __device__ __forceinline__ uint32_t fin(uint32_t v) const
+    {
+        if (DETECT) wsf |= (v - 0x21212121u) & ~v;
+        return UPPER ? upper4(v) : v;
+    }
+    __device__ __forceinline__ bool saw_ws_candidate() const { return DETECT && (wsf & 0x80808080u) != 0; }
     __device__ __forceinline__ uint32_t u32be(uint32_t off) const
     {
         const uint32_t *q = w + (off >> 2);
-        uint32_t v = __byte_perm(q[0], q[1], besel);
-        return UPPER ? upper4(v) : v;
+        return fin(__byte_perm(q[0], q[1], besel));
     }
     __device__ __forceinline__ uint32_t u32(uint32_t off) const
     {
         const uint32_t *q = w + (off >> 2);
-        uint32_t v = __funnelshift_r(q[0], q[1], sh);
-        return UPPER ? upper4(v) : v;
+        return fin(__funnelshift_r(q[0], q[1], sh));
     }
     __device__ __forceinline__ uint32_t u32x(uint32_t off) const
     {
         uint32_t a = off + bo;
         const uint32_t *q = w + (a >> 2);
-        uint32_t v = __funnelshift_r(q[0], q[1], (a & 3) * 8);
-        return UPPER ? upper4(v) : v;
+        return fin(__funnelshift_r(q[0], q[1], (a & 3) * 8));
     }
     __device__ __forceinline__ uint64_t u64(uint32_t off) const { return mk64(u32(off), u32(off + 4)); }
     __device__ __forceinline__ uint64_t u64x(uint32_t off) const
@@ -131,9 +138,7 @@ struct SmemReader {
         const uint32_t *q = w + (a >> 2);
         uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
         uint32_t s = (a & 3) * 8;
-        uint32_t lo = __funnelshift_r(w0, w1, s), hi = __funnelshift_r(w1, w2, s);
-        if (UPPER) { lo = upper4(lo); hi = upper4(hi); }
-        return mk64(lo, hi);
+        return mk64(fin(__funnelshift_r(w0, w1, s)), fin(__funnelshift_r(w1, w2, s)));
     }
     __device__ __forceinline__ uint32_t u8(uint32_t off) const { return u32x(off) & 0xffu; }
 };

@@ -55,14 +55,8 @@ constexpr uint32_t TMA_CHUNK = 32768;   // one bulk copy moves at most this many
 __device__ __forceinline__ uint32_t has_byte_below_0x21(uint32_t w) { return (w - 0x21212121u) & ~w & 0x80808080u; }
 
 // compact the record [start, start+len) of the tile in place; returns the new length
-__device__ __forceinline__ uint32_t strip_in_smem(uint8_t *tile, uint32_t start, uint32_t len)
+__device__ __noinline__ uint32_t strip_in_smem(uint8_t *tile, uint32_t start, uint32_t len)
 {
-    // cheap test first: aligned words covering the record (neighbouring bytes can only cause a false alarm)
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + (start & ~3u));
-    const uint32_t nw = ((start & 3u) + len + 3u) >> 2;
-    uint32_t f = 0;
-    for (uint32_t k = 0; k < nw; k++) f |= has_byte_below_0x21(wp[k]);
-    if (!f) return len;
     uint32_t j = start;
     for (uint32_t i = start; i < start + len; i++) {
         const uint8_t c = tile[i];
@@ -83,16 +77,19 @@ __device__ __forceinline__ uint32_t strip_to_scratch(const uint8_t *__restrict__
     return j;
 }
 
-// strip_scratch != nullptr turns the whitespace strip on: the staged tile is tested once (cooperatively)
-// for any byte < 0x21; only if one exists do the threads compact their own records in shared memory.
-// out_len (may be null) receives the post-strip length of every record.
-template <uint32_t MASK, bool UPPER>
+// STRIP fuses the whitespace strip (seqhasher.go:246) into the tile pass without a second look at the data:
+// the readers OR a "byte < 0x21" test into a flag while the record is being hashed (for a fused set with
+// upper-casing the flag comes from the in-place upper pass instead); only a record that really holds such a
+// byte is compacted in shared memory and hashed again.  out_len (may be null) receives the post-strip lengths.
+template <uint32_t MASK, bool UPPER, bool STRIP>
 __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restrict__ res,
                                                         const int64_t *__restrict__ offs, size_t n, OutPtrs out,
                                                         uint32_t rmask, uint32_t cap, uint8_t *strip_scratch,
                                                         int64_t *__restrict__ out_len)
 {
     constexpr bool MULTI = (MASK & (MASK - 1)) != 0;
+    constexpr bool INPLACE = MULTI && UPPER;          // tile upper-cased in place by a cooperative pass
+    constexpr bool SPECULATE = STRIP && !INPLACE;     // whitespace candidates detected by the readers
     extern __shared__ __align__(128) uint8_t tile[];   // cap + 32 bytes
     __shared__ uint64_t mbar;
 
@@ -104,12 +101,12 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     int64_t s = 0, e = 0;
     if (i < n) { s = offs[i]; e = offs[i + 1]; }
     uint32_t len = (uint32_t)(e - s);
-    const bool strip = strip_scratch != nullptr;
     const int64_t a0 = t_start & ~(int64_t)15;            // residue base is 16-byte aligned
     const int64_t span = (t_end - a0 + 15) & ~(int64_t)15;
 
     if (span <= (int64_t)cap) {
         const uint32_t bytes = (uint32_t)span;
+        const uint32_t start = (uint32_t)(s - a0);
         if (bytes) {
             if (threadIdx.x == 0) mbar_init(&mbar, 1);
             __syncthreads();
@@ -119,31 +116,33 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
                     tma_bulk_g2s(tile + o, res + a0 + o, (bytes - o < TMA_CHUNK) ? bytes - o : TMA_CHUNK, &mbar);
             }
             mbar_wait(&mbar, 0);
-            if ((MULTI && UPPER) || strip) {
-                // one cooperative pass over the tile: upper-case in place when several hashes will read
-                // it (seqhasher.go:249-251), and look for whitespace candidates (seqhasher.go:246)
+            if (INPLACE) {
+                // one cooperative pass: upper-case in place once for every hash of the set (seqhasher.go:249-251)
+                // and, when stripping, look for whitespace candidates on the way
                 uint4 *t4 = reinterpret_cast<uint4 *>(tile);
                 uint32_t f = 0;
                 for (uint32_t k = threadIdx.x; k < (bytes >> 4); k += blockDim.x) {
                     uint4 v = t4[k];
-                    if (strip) f |= has_byte_below_0x21(v.x) | has_byte_below_0x21(v.y) | has_byte_below_0x21(v.z) |
+                    if (STRIP) f |= has_byte_below_0x21(v.x) | has_byte_below_0x21(v.y) | has_byte_below_0x21(v.z) |
                                     has_byte_below_0x21(v.w);
-                    if (MULTI && UPPER) {
-                        v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w);
-                        t4[k] = v;
-                    }
+                    v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w);
+                    t4[k] = v;
                 }
-                const int any_ws = __syncthreads_or(strip && f != 0);
-                if (any_ws && i < n && len) len = strip_in_smem(tile, (uint32_t)(s - a0), len);
+                const int any_ws = __syncthreads_or(STRIP && f != 0);
+                if (STRIP && any_ws && i < n && len) len = strip_in_smem(tile, start, len);
             }
         }
         if (i < n) {
-            if (strip && out_len) out_len[i] = len;
-            SmemReader<UPPER && !MULTI> r(tile, (uint32_t)(s - a0));
-            hash_set<MASK>(r, len, i, out, rmask);
+            for (int pass = 0;; pass++) {
+                SmemReader<UPPER && !MULTI, SPECULATE> r(tile, start);
+                hash_set<MASK>(r, len, i, out, rmask);
+                if (!SPECULATE || pass == 1 || !r.saw_ws_candidate()) break;
+                len = strip_in_smem(tile, start, len);   // rare: compact this record, hash it again
+            }
+            if (STRIP && out_len) out_len[i] = len;
         }
     } else if (i < n) {
-        if (strip) {
+        if (STRIP) {
             len = strip_to_scratch(res, strip_scratch, s, len);
             if (out_len) out_len[i] = len;
             GlobalReader<UPPER, false> r(strip_scratch, s);   // written by this thread just above
@@ -160,25 +159,29 @@ constexpr uint32_t FAST_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_CITYHASH) | b
                                bit(A_RAPIDHASH) | bit(A_RAPIDHASH32);
 constexpr uint32_t C3_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_MURMUR3);
 
-template <uint32_t MASK>
-static cudaError_t launch_tile_t(bool upper, const uint8_t *res, const int64_t *offs, size_t n, const OutPtrs &out,
-                                 uint32_t rmask, uint32_t cap, uint8_t *strip_scratch, int64_t *out_len, cudaStream_t st)
+template <uint32_t MASK, bool UPPER, bool STRIP>
+static cudaError_t launch_tile_k(const uint8_t *res, const int64_t *offs, size_t n, const OutPtrs &out, uint32_t rmask,
+                                 uint32_t cap, uint8_t *strip_scratch, int64_t *out_len, cudaStream_t st)
 {
     const unsigned threads = 128;
     const size_t blocks = (n + threads - 1) / threads;
     const size_t smem = (size_t)cap + 32;
-    cudaError_t e;
-    if (upper) {
-        e = cudaFuncSetAttribute(hash_tile_kernel<MASK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        hash_tile_kernel<MASK, true><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap, strip_scratch, out_len);
-    } else {
-        e = cudaFuncSetAttribute(hash_tile_kernel<MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        hash_tile_kernel<MASK, false><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap, strip_scratch, out_len);
-    }
+    cudaError_t e = cudaFuncSetAttribute(hash_tile_kernel<MASK, UPPER, STRIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hash_tile_kernel<MASK, UPPER, STRIP><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap, strip_scratch, out_len);
     g_launches++;
     return cudaGetLastError();
+}
+
+template <uint32_t MASK>
+static cudaError_t launch_tile_t(bool upper, const uint8_t *res, const int64_t *offs, size_t n, const OutPtrs &out,
+                                 uint32_t rmask, uint32_t cap, uint8_t *strip_scratch, int64_t *out_len, cudaStream_t st)
+{
+    if (strip_scratch)
+        return upper ? launch_tile_k<MASK, true, true>(res, offs, n, out, rmask, cap, strip_scratch, out_len, st)
+                     : launch_tile_k<MASK, false, true>(res, offs, n, out, rmask, cap, strip_scratch, out_len, st);
+    return upper ? launch_tile_k<MASK, true, false>(res, offs, n, out, rmask, cap, nullptr, out_len, st)
+                 : launch_tile_k<MASK, false, false>(res, offs, n, out, rmask, cap, nullptr, out_len, st);
 }
 
 // Hash every algorithm of `mask` (bit a = algo a) over the batch; outs[a] is the digest array of algo a.
