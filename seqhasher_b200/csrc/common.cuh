@@ -28,6 +28,13 @@ __device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((ui
 // lo64(a*b) ^ hi64(a*b): the "fold" of xxh3 / rapidhash
 __device__ __forceinline__ uint64_t mulfold64(uint64_t a, uint64_t b) { return (a * b) ^ __umul64hi(a, b); }
 
+// The multiplier 1 as a value ptxas cannot see (a __constant__ may be rewritten by the host, so loads
+// of it are never folded): x * c_one + y is an IMAD on the FMA pipe instead of an IADD3 on the ALU pipe.
+// sm_100 issues LOP3/SHF/PRMT/IADD3 only on the ALU pipe (64 lanes/clk/SM); the FMA pipe (IMAD, another
+// 64 lanes/clk/SM) is idle in the integer hashes, so moving adds there shortens the ALU-bound kernels.
+static __constant__ uint32_t c_one = 1u;
+__device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t y) { return x * c_one + y; }
+
 // ASCII upper-casing of 4 packed bytes (a-z -> A-Z, everything else untouched, bytes >= 0x80 too).
 __device__ __forceinline__ uint32_t upper4(uint32_t x)
 {

@@ -24,10 +24,11 @@ enum : uint32_t { B3_CHUNK_START = 1, B3_CHUNK_END = 2, B3_PARENT = 4, B3_ROOT =
 
 __device__ __forceinline__ void b3_g(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d, uint32_t mx, uint32_t my)
 {
-    a = a + b + mx; d = rotr32(d ^ a, 16);
-    c = c + d;      b = rotr32(b ^ c, 12);
-    a = a + b + my; d = rotr32(d ^ a, 8);
-    c = c + d;      b = rotr32(b ^ c, 7);
+    // the message-word adds are forced onto the FMA pipe (fma_add): BLAKE3 is ALU-pipe bound on sm_100
+    a = fma_add(a + b, mx); d = rotr32(d ^ a, 16);
+    c = c + d;              b = rotr32(b ^ c, 12);
+    a = fma_add(a + b, my); d = rotr32(d ^ a, 8);
+    c = c + d;              b = rotr32(b ^ c, 7);
 }
 
 // message word schedule: round r uses m[SCHED[r][i]] (the spec's permutation applied r times)

@@ -61,10 +61,6 @@ __device__ __forceinline__ void sha1_compress_v(uint32_t (&h)[5], uint32_t (&w)[
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
 }
 
-// The multiplier 1 as a value ptxas cannot see (a __constant__ may be rewritten by the host, so loads
-// of it are never folded): x * c_one + y is an IMAD on the FMA pipe instead of an IADD3 on the ALU pipe.
-static __constant__ uint32_t c_one = 1u;
-
 // Production form = variant 8 (measured fastest on B200, tools/probe_sha1_variants.py): only the
 // W[t]+K adds are forced onto the FMA pipe, which also makes ptxas emit the remaining two-input adds as
 // IMAD.IADD; IMAD.WIDE-based rotates are slower than SHF and stay off.

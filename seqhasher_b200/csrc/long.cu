@@ -187,20 +187,39 @@ __global__ void __launch_bounds__(128) b3_chunks_kernel(const uint8_t *__restric
     const uint32_t nchunks = (uint32_t)((len + 1023) >> 10);
     const uint32_t clen = (c + 1 < nchunks) ? 1024u : (uint32_t)(len - ((int64_t)c << 10));
     const uint32_t root = (nchunks == 1) ? (uint32_t)B3_ROOT : 0u;
+    // One loop for every lane of the warp: full 64-byte blocks take the aligned 128-bit loads, the single
+    // partial block of a record's last chunk takes masked reads, and the compression (the expensive part)
+    // is issued once per iteration for all lanes whatever their chunk length.
     uint32_t cv[8];
-    if (clen == 1024u) {
-        const uint8_t *p = res + s + ((int64_t)c << 10);
-        b3_set_iv(cv);
+    b3_set_iv(cv);
+    const int64_t cbase = s + ((int64_t)c << 10);
+    const uint32_t nblocks = clen ? (clen + 63) >> 6 : 1;
 #pragma unroll 1
-        for (uint32_t b = 0; b < 16; b++) {
+    for (uint32_t b = 0; b < 16; b++) {
+        if (b < nblocks) {
             uint32_t m[16];
-            load_block16<UPPER>(p + 64 * b, m);
-            const uint32_t flags = (b == 0 ? (uint32_t)B3_CHUNK_START : 0u) | (b == 15 ? ((uint32_t)B3_CHUNK_END | root) : 0u);
-            b3_compress(cv, m, c, 0u, 64u, flags);
+            const uint32_t off = b << 6;
+            uint32_t bl = 64;
+            if (off + 64 <= clen) {
+                load_block16<UPPER>(res + cbase + off, m);
+            } else {
+                bl = clen - off;
+                GlobalReader<UPPER> r(res, cbase);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t o = off + 4 * k;
+                    uint32_t v = 0;
+                    if (o < clen) {
+                        v = r.u32(o);
+                        if (o + 4 > clen) v &= (1u << (8 * (clen - o))) - 1u;
+                    }
+                    m[k] = v;
+                }
+            }
+            const uint32_t flags = (b == 0 ? (uint32_t)B3_CHUNK_START : 0u) |
+                                   (b == nblocks - 1 ? ((uint32_t)B3_CHUNK_END | root) : 0u);
+            b3_compress(cv, m, c, 0u, bl, flags);
         }
-    } else {
-        GlobalReader<UPPER> r(res, s);
-        b3_chunk_cv(r, c << 10, clen, c, root, cv);
     }
     uint32_t *dst = root ? reinterpret_cast<uint32_t *>(out + i * 32) : cvs + g * 8;
     *reinterpret_cast<uint4 *>(dst) = make_uint4(cv[0], cv[1], cv[2], cv[3]);
