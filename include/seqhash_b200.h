@@ -49,7 +49,8 @@ enum shb_algo {
 #define SHB_ERR_BAD_ARG (-2)
 #define SHB_ERR_CAPACITY (-3)    /* batch larger than the capacity given to shb_batch_create */
 #define SHB_ERR_CUDA (-4)        /* a CUDA call failed; see shb_last_error() */
-#define SHB_ERR_OFFSETS (-5)     /* offsets not monotone / record longer than 2^32-1 bytes */
+#define SHB_ERR_OFFSETS (-5)     /* offsets not monotone / record longer than 2^31-1 bytes */
+#define SHB_ERR_FORMAT (-6)      /* text is not FASTA/FASTQ ("fastx: invalid FASTA/Q format") */
 
 /* Library lifetime.  n_gpus <= 0 uses every visible device; devices 0..n-1 otherwise.  Returns the
  * number of devices in use (>0) or an error.  Idempotent. */
@@ -115,6 +116,36 @@ int shb_hash_device(int device, const uint8_t *d_residues, const int64_t *d_offs
 
 /* Number of kernels this library has launched in this process (monotone; for bench accounting). */
 unsigned long long shb_launch_count(void);
+
+/* ---- whole record loop on the GPU: raw FASTA/FASTQ text in, output text out ----
+ *
+ * Replaces the entire body of processSequences' loop (seqhasher.go:227-283) for one chunk of DECOMPRESSED
+ * text: record splitting with the reader semantics of bio's fastx (seqhasher.go:221-239; FASTA records start
+ * at a line-initial '>', FASTQ is strict 4-line), whitespace strip (:246), upper-casing (:249-251), the
+ * hashes (:255-259), the header rewrite `file;h1;..;hn;Name` (:261-272) and --headersonly / record.Format(0)
+ * output (:274-282).  The host keeps file I/O and decompression only.
+ *
+ * Protocol: write up to shb_textproc_capacity() bytes into shb_textproc_input(), starting at a record marker
+ * (the host skips leading blank lines and sniffs the format from the first byte: '>' FASTA, '@' FASTQ, else
+ * the reference's "fastx: invalid FASTA/Q format" error); call shb_textproc_run (blocking); write
+ * shb_textproc_output() to the sink; move the unconsumed tail (input + shb_textproc_consumed()) to the front
+ * and refill.  is_final = this chunk ends the input (a missing last line break is added).  label = the file
+ * name field (cfg.inputFileName or --name), NULL for --nofilename / stdin.  flags: SHB_FLAG_UPPER only (the
+ * splitter always strips).  shb_textproc_empty_records() = records with an empty sequence, for which the
+ * reference logs one line per hash type (seqhasher.go:293). */
+#define SHB_FORMAT_FASTA 1
+#define SHB_FORMAT_FASTQ 2
+typedef struct shb_textproc shb_textproc;
+shb_textproc *shb_textproc_create(int device, size_t max_text_bytes);
+void shb_textproc_destroy(shb_textproc *t);
+uint8_t *shb_textproc_input(shb_textproc *t);
+size_t shb_textproc_capacity(shb_textproc *t);
+int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, const int *algos, int n_algos,
+                     unsigned flags, int headers_only, const char *label);
+const uint8_t *shb_textproc_output(shb_textproc *t, size_t *out_bytes);
+size_t shb_textproc_consumed(shb_textproc *t);
+size_t shb_textproc_records(shb_textproc *t);
+size_t shb_textproc_empty_records(shb_textproc *t);
 
 /* ---- measurement helpers (not part of the hashing path) ---- */
 

@@ -27,8 +27,12 @@ EXPORTS = [
     "shb_digest_size", "shb_batch_create", "shb_batch_create_on", "shb_batch_destroy", "shb_batch_residues",
     "shb_batch_offsets", "shb_submit", "shb_wait", "shb_digests", "shb_out_lengths", "shb_out_offsets",
     "shb_out_residues", "shb_scratch_bytes", "shb_hash_device", "shb_launch_count", "shb_synth_fill",
-    "shb_probe_int_peak", "shb_probe_last_checksum",
+    "shb_probe_int_peak", "shb_probe_last_checksum", "shb_textproc_create", "shb_textproc_destroy",
+    "shb_textproc_input", "shb_textproc_capacity", "shb_textproc_run", "shb_textproc_output", "shb_textproc_consumed",
+    "shb_textproc_records", "shb_textproc_empty_records",
 ]
+FORMAT_FASTA = 1
+FORMAT_FASTQ = 2
 
 
 class SeqhashError(RuntimeError):
@@ -75,6 +79,16 @@ def lib() -> ctypes.CDLL:
     L.shb_synth_fill.restype = c.c_int
     L.shb_probe_int_peak.argtypes = [c.c_int, c.c_int, c.c_int]; L.shb_probe_int_peak.restype = c.c_double
     L.shb_probe_last_checksum.argtypes = []; L.shb_probe_last_checksum.restype = c.c_uint
+    L.shb_textproc_create.argtypes = [c.c_int, c.c_size_t]; L.shb_textproc_create.restype = c.c_void_p
+    L.shb_textproc_destroy.argtypes = [c.c_void_p]; L.shb_textproc_destroy.restype = None
+    L.shb_textproc_input.argtypes = [c.c_void_p]; L.shb_textproc_input.restype = c.c_void_p
+    L.shb_textproc_capacity.argtypes = [c.c_void_p]; L.shb_textproc_capacity.restype = c.c_size_t
+    L.shb_textproc_run.argtypes = [c.c_void_p, c.c_size_t, c.c_int, c.c_int, c.POINTER(c.c_int), c.c_int, c.c_uint, c.c_int,
+                                   c.c_char_p]
+    L.shb_textproc_run.restype = c.c_int
+    L.shb_textproc_output.argtypes = [c.c_void_p, c.POINTER(c.c_size_t)]; L.shb_textproc_output.restype = c.c_void_p
+    for nm in ("shb_textproc_consumed", "shb_textproc_records", "shb_textproc_empty_records"):
+        getattr(L, nm).argtypes = [c.c_void_p]; getattr(L, nm).restype = c.c_size_t
     _lib = L
     return L
 
@@ -227,3 +241,39 @@ def probe_int_peak(kind: int, iters: int = 2000, device: int = 0) -> float:
 
 def probe_last_checksum() -> int:
     return lib().shb_probe_last_checksum()
+
+
+class TextProc:
+    """shb_textproc: the whole record loop of processSequences on the GPU for chunks of decompressed text."""
+
+    def __init__(self, max_text_bytes: int = 64 << 20, device: int = 0):
+        L = lib()
+        self._h = L.shb_textproc_create(device, max_text_bytes)
+        if not self._h:
+            raise SeqhashError(f"shb_textproc_create failed: {L.shb_last_error().decode()}")
+        self.capacity = L.shb_textproc_capacity(self._h)
+        p = L.shb_textproc_input(self._h)
+        self.input = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(self.capacity + 32,))
+
+    def close(self) -> None:
+        if self._h:
+            lib().shb_textproc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, n_bytes: int, fmt: int, is_final: bool, algos, flags: int, headers_only: bool, label: bytes | None):
+        """Returns (output bytes view, consumed, n_records, n_empty).  The view is valid until the next run."""
+        L = lib()
+        ids = list(algos)
+        arr = (ctypes.c_int * max(len(ids), 1))(*ids)
+        _check(L.shb_textproc_run(self._h, n_bytes, fmt, 1 if is_final else 0, arr, len(ids), flags,
+                                  1 if headers_only else 0, label), "shb_textproc_run")
+        nb = ctypes.c_size_t(0)
+        p = L.shb_textproc_output(self._h, ctypes.byref(nb))
+        out = ctypes.string_at(p, nb.value) if nb.value else b""
+        return out, L.shb_textproc_consumed(self._h), L.shb_textproc_records(self._h), L.shb_textproc_empty_records(self._h)

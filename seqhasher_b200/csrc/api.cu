@@ -10,6 +10,7 @@
 
 #include "../../include/seqhash_b200.h"
 #include "kernels.cuh"
+#include "parse.cuh"
 
 namespace {
 
@@ -416,5 +417,170 @@ double shb_probe_int_peak(int device, int kind, int iters)
     cudaFree(sink);
     return best;
 }
+
+// ---- whole-record-loop path: raw FASTA/FASTQ text in, formatted output text out ----
+
+struct shb_textproc {
+    int device = 0;
+    size_t cap = 0;
+    long long max_records = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t *h_text = nullptr, *d_text = nullptr, *d_res = nullptr;
+    void *d_parse_scratch = nullptr;
+    shb::FxOut rec{};
+    shb::FxInfo *d_info = nullptr, *h_info = nullptr;
+    uint32_t *d_out_len = nullptr;
+    long long *d_out_off = nullptr;
+    uint8_t *d_label = nullptr;
+    uint8_t *d_dig = nullptr;
+    size_t dig_cap = 0;
+    void *d_scratch = nullptr;
+    size_t scratch_cap = 0;
+    uint8_t *d_out = nullptr, *h_out = nullptr;
+    size_t out_cap = 0;
+    // results of the last run
+    size_t out_bytes = 0, consumed = 0, n_records = 0, n_empty = 0;
+};
+
+shb_textproc *shb_textproc_create(int device, size_t max_text_bytes)
+{
+    if (g_ndev == 0 && shb_init(0, 0) < 0) return nullptr;
+    if (device < 0 || device >= g_ndev || max_text_bytes == 0 || max_text_bytes >= ((size_t)1 << 40)) {
+        fail(SHB_ERR_BAD_ARG, "bad device or capacity");
+        return nullptr;
+    }
+    shb_textproc *t = new shb_textproc();
+    t->device = device;
+    t->cap = max_text_bytes;
+    t->max_records = (long long)(max_text_bytes / 16 + 1024);
+    const size_t nr = (size_t)t->max_records;
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaHostAlloc(&t->h_text, max_text_bytes + 64, cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc(&t->h_info, sizeof(shb::FxInfo) + 64, cudaHostAllocDefault) == cudaSuccess &&
+              cudaMalloc(&t->d_text, max_text_bytes + 64) == cudaSuccess &&
+              cudaMalloc(&t->d_res, max_text_bytes + 64) == cudaSuccess &&
+              cudaMalloc(&t->d_parse_scratch, shb::fx_scratch_bytes(max_text_bytes)) == cudaSuccess &&
+              cudaMalloc(&t->d_info, sizeof(shb::FxInfo)) == cudaSuccess &&
+              cudaMalloc(&t->rec.offsets, (nr + 1) * 8) == cudaSuccess && cudaMalloc(&t->rec.name_start, nr * 8) == cudaSuccess &&
+              cudaMalloc(&t->rec.name_len, nr * 4) == cudaSuccess && cudaMalloc(&t->rec.qual_start, nr * 8) == cudaSuccess &&
+              cudaMalloc(&t->rec.qual_len, nr * 4) == cudaSuccess && cudaMalloc(&t->rec.rec_start, (nr + 1) * 8) == cudaSuccess &&
+              cudaMalloc(&t->d_out_len, (nr + 1) * 4) == cudaSuccess && cudaMalloc(&t->d_out_off, (nr + 1) * 8) == cudaSuccess &&
+              cudaMalloc(&t->d_label, 4096) == cudaSuccess;
+    if (!ok) {
+        fail(SHB_ERR_CUDA, std::string("textproc allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+        shb_textproc_destroy(t);
+        return nullptr;
+    }
+    t->rec.residues = t->d_res;
+    t->rec.max_records = t->max_records;
+    return t;
+}
+
+void shb_textproc_destroy(shb_textproc *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->stream) { cudaStreamSynchronize(t->stream); cudaStreamDestroy(t->stream); }
+    cudaFreeHost(t->h_text); cudaFreeHost(t->h_info); cudaFreeHost(t->h_out);
+    cudaFree(t->d_text); cudaFree(t->d_res); cudaFree(t->d_parse_scratch); cudaFree(t->d_info);
+    cudaFree(t->rec.offsets); cudaFree(t->rec.name_start); cudaFree(t->rec.name_len); cudaFree(t->rec.qual_start);
+    cudaFree(t->rec.qual_len); cudaFree(t->rec.rec_start); cudaFree(t->d_out_len); cudaFree(t->d_out_off);
+    cudaFree(t->d_label); cudaFree(t->d_dig); cudaFree(t->d_scratch); cudaFree(t->d_out);
+    delete t;
+}
+
+uint8_t *shb_textproc_input(shb_textproc *t) { return t ? t->h_text : nullptr; }
+size_t shb_textproc_capacity(shb_textproc *t) { return t ? t->cap : 0; }
+
+int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, const int *algos, int n_algos,
+                     unsigned flags, int headers_only, const char *label)
+{
+    if (!t) return fail(SHB_ERR_BAD_ARG, "null textproc");
+    if (int rc = check_algos(algos, n_algos)) return rc;
+    if (n_algos > SHB_N_ALGOS * 4) return fail(SHB_ERR_BAD_ARG, "too many hash types");
+    if (n_bytes > t->cap) return fail(SHB_ERR_CAPACITY, "text larger than the textproc capacity");
+    if (format != SHB_FORMAT_FASTA && format != SHB_FORMAT_FASTQ) return fail(SHB_ERR_BAD_ARG, "format must be FASTA or FASTQ");
+    const size_t label_len = label ? std::strlen(label) : 0;
+    if (label_len > 4096) return fail(SHB_ERR_BAD_ARG, "label too long");
+    CU(cudaSetDevice(t->device));
+    t->out_bytes = t->consumed = t->n_records = t->n_empty = 0;
+    if (n_bytes == 0) return SHB_OK;
+    if (is_final && t->h_text[n_bytes - 1] != '\n') t->h_text[n_bytes++] = '\n';   // the pinned buffer has 64 spare bytes
+    std::memset(t->h_text + n_bytes, 0, 32);
+    cudaStream_t st = t->stream;
+    CU(cudaMemcpyAsync(t->d_text, t->h_text, align_up(n_bytes + 16, 16), cudaMemcpyHostToDevice, st));
+    if (label_len) CU(cudaMemcpyAsync(t->d_label, label, label_len, cudaMemcpyHostToDevice, st));
+    // 1. split into records (CSR residues + name / quality spans)
+    CU(shb::launch_fx_parse(t->d_text, n_bytes, format == SHB_FORMAT_FASTQ, is_final != 0, t->rec, t->d_info, t->d_parse_scratch, st));
+    CU(cudaMemcpyAsync(t->h_info, t->d_info, sizeof(shb::FxInfo), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (t->h_info->status == shb::FX_BAD_MARKER) return fail(SHB_ERR_FORMAT, "fastx: invalid FASTA/Q format");
+    if (t->h_info->status == shb::FX_TOO_MANY_RECORDS) return fail(SHB_ERR_CAPACITY, "more records than the textproc can index; use smaller chunks");
+    const size_t n = (size_t)t->h_info->n_records, total = (size_t)t->h_info->n_residues;
+    t->n_records = n;
+    t->consumed = (size_t)t->h_info->consumed;
+    if (n == 0) return SHB_OK;
+    // 2. hash (the residues are already whitespace-free; upper-casing is fused into the hash kernels)
+    std::vector<size_t> slot_off(n_algos + 1, 0);
+    for (int k = 0; k < n_algos; k++) slot_off[k + 1] = slot_off[k] + align_up(n * shb::digest_size(algos[k]), 256);
+    if (slot_off[n_algos] > t->dig_cap) {
+        cudaFree(t->d_dig);
+        t->d_dig = nullptr; t->dig_cap = 0;
+        CU(cudaMalloc(&t->d_dig, slot_off[n_algos]));
+        t->dig_cap = slot_off[n_algos];
+    }
+    const size_t sneed = ScratchLayout(t->cap, (size_t)t->max_records).total;
+    if (sneed > t->scratch_cap) {
+        cudaFree(t->d_scratch);
+        t->d_scratch = nullptr; t->scratch_cap = 0;
+        CU(cudaMalloc(&t->d_scratch, sneed));
+        t->scratch_cap = sneed;
+    }
+    std::vector<uint8_t *> d_slots(n_algos);
+    for (int k = 0; k < n_algos; k++) d_slots[k] = t->d_dig + slot_off[k];
+    if (int rc = run_pipeline(t->d_res, reinterpret_cast<const int64_t *>(t->rec.offsets), n, total, algos, n_algos,
+                              flags & SHB_FLAG_UPPER, d_slots.data(), nullptr, t->d_scratch, st, nullptr, nullptr))
+        return rc;
+    // 3. format: `file;h1;..;hn;Name` (+ record body), seqhasher.go:261-282
+    shb::FmtCfg cfg{};
+    cfg.label = t->d_label;
+    cfg.label_len = label ? (int)label_len : -1;
+    cfg.n_algos = n_algos > SHB_N_ALGOS ? SHB_N_ALGOS : n_algos;
+    if (n_algos > SHB_N_ALGOS) return fail(SHB_ERR_BAD_ARG, "at most 12 hash fields per record in the GPU formatter");
+    for (int k = 0; k < n_algos; k++) { cfg.dsize[k] = shb::digest_size(algos[k]); cfg.digests[k] = d_slots[k]; }
+    cfg.headers_only = headers_only;
+    cfg.fastq = format == SHB_FORMAT_FASTQ;
+    cfg.upper = (flags & SHB_FLAG_UPPER) ? 1 : 0;
+    CU(shb::launch_fx_format(cfg, t->rec, n, t->d_text, t->d_out_len, t->d_out_off, nullptr, t->d_info, true, st));
+    CU(cudaMemcpyAsync(&t->h_info->reserved, t->d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&t->h_info->n_empty, &t->d_info->n_empty, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const size_t out_bytes = (size_t)t->h_info->reserved;
+    t->n_empty = (size_t)t->h_info->n_empty;
+    if (out_bytes > t->out_cap) {
+        cudaFree(t->d_out); cudaFreeHost(t->h_out);
+        t->d_out = nullptr; t->h_out = nullptr; t->out_cap = 0;
+        const size_t want = out_bytes + out_bytes / 4 + 4096;
+        CU(cudaMalloc(&t->d_out, want));
+        CU(cudaHostAlloc(&t->h_out, want, cudaHostAllocDefault));
+        t->out_cap = want;
+    }
+    CU(shb::launch_fx_format(cfg, t->rec, n, t->d_text, t->d_out_len, t->d_out_off, t->d_out, t->d_info, false, st));
+    CU(cudaMemcpyAsync(t->h_out, t->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    t->out_bytes = out_bytes;
+    return SHB_OK;
+}
+
+const uint8_t *shb_textproc_output(shb_textproc *t, size_t *out_bytes)
+{
+    if (!t) return nullptr;
+    if (out_bytes) *out_bytes = t->out_bytes;
+    return t->h_out;
+}
+size_t shb_textproc_consumed(shb_textproc *t) { return t ? t->consumed : 0; }
+size_t shb_textproc_records(shb_textproc *t) { return t ? t->n_records : 0; }
+size_t shb_textproc_empty_records(shb_textproc *t) { return t ? t->n_empty : 0; }
 
 }  // extern "C"

@@ -1,0 +1,400 @@
+// parse.cu — FASTA/FASTQ record splitter and output formatter on the GPU: the callers either side of the
+// hash path (north_star "a FASTA/FASTQ newline scan with a prefix sum that finds
+// record and line boundaries and strips line breaks").
+//
+// Splitter.  Reader semantics follow what the reference gets from bio's fastx reader (seqhasher.go:221-239;
+// SURVEY.md App. B): FASTA — a record starts at '>' at the beginning of a line, its name is the rest of that
+// line, its sequence every following byte up to the next line-initial '>'; FASTQ — strict 4-line records.
+// Whitespace is dropped while compacting (line breaks by the reader, blanks by seqhasher.go:246), so the CSR
+// batch that comes out is already stripped.  The text must start at the first record marker and, when it is
+// the last chunk of the input, end with '\n' (the host wrapper guarantees both).
+//   pass 1  fx_lines_kernel     : per 4 KiB block, position of its last '\n' and its '\n' count
+//   scan    fx_scan_kernel      : exclusive prefix (max position, sum of counts) over the blocks
+//   pass 2  fx_emit_kernel<..,true>  : classify every byte with its line state -> kept-byte / record counts
+//   scan    scan_counts x2
+//   pass 3  fx_emit_kernel<..,false> : same classification, then scatter the residues and the per-record
+//           fields (sequence offset, name span, quality span)
+//   fx_finish_kernel            : record count, closing offset, bytes consumed (chunked input)
+// Formatter.  fmt_len_kernel + scan_counts + fmt_write_kernel build the output of seqhasher.go:261-282
+// (`file;h1;..;hn;Name`, --headersonly, record.Format(0) for FASTA/FASTQ), hex encoding included.
+#include "hash_all.cuh"
+#include "parse.cuh"
+
+namespace shb {
+
+constexpr int FX_THREADS = 256;   // 16 bytes per thread, FX_BLK = 4096
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], int j) { return (w[j >> 2] >> (8 * (j & 3))) & 0xffu; }
+
+__global__ void __launch_bounds__(FX_THREADS) fx_lines_kernel(const uint8_t *__restrict__ text, size_t n,
+                                                              long long *__restrict__ blk_last_nl,
+                                                              uint32_t *__restrict__ blk_nl_count)
+{
+    const size_t pos = (size_t)blockIdx.x * FX_BLK + 16u * threadIdx.x;
+    long long last = -1;
+    uint32_t cnt = 0;
+    if (pos < n) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + pos));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (pos + j < n && byte_of(w, j) == '\n') { last = (long long)(pos + j); cnt++; }
+    }
+    __shared__ long long s_last[FX_THREADS / 32];
+    __shared__ uint32_t s_cnt[FX_THREADS / 32];
+    for (int d = 16; d; d >>= 1) {
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    }
+    if ((threadIdx.x & 31) == 0) { s_last[threadIdx.x >> 5] = last; s_cnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < FX_THREADS / 32; k++) { last = max(last, s_last[k]); cnt += s_cnt[k]; }
+        blk_last_nl[blockIdx.x] = last;
+        blk_nl_count[blockIdx.x] = cnt;
+    }
+}
+
+// Exclusive prefixes over the nb blocks (one CTA; thread t owns a contiguous run of blocks):
+// prev_nl[b] = max last_nl over blocks < b (-1 if none), nl_before[b] = newline count of blocks < b;
+// element nb holds the totals.
+__global__ void __launch_bounds__(1024) fx_scan_kernel(const long long *__restrict__ blk_last_nl,
+                                                       const uint32_t *__restrict__ blk_nl_count, size_t nb,
+                                                       long long *__restrict__ prev_nl, long long *__restrict__ nl_before)
+{
+    __shared__ long long s_mx[1024], s_sum[1024];
+    const size_t per = (nb + 1023) / 1024;
+    const size_t lo = (size_t)threadIdx.x * per;
+    const size_t hi = lo + per < nb ? lo + per : nb;
+    long long mx = -1, sum = 0;
+    for (size_t i = lo; i < hi; i++) { mx = max(mx, blk_last_nl[i]); sum += blk_nl_count[i]; }
+    s_mx[threadIdx.x] = mx;
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 per-thread summaries
+    for (int d = 1; d < 1024; d <<= 1) {
+        long long a = -1, b = 0;
+        if ((int)threadIdx.x >= d) { a = s_mx[threadIdx.x - d]; b = s_sum[threadIdx.x - d]; }
+        __syncthreads();
+        if ((int)threadIdx.x >= d) { s_mx[threadIdx.x] = max(s_mx[threadIdx.x], a); s_sum[threadIdx.x] += b; }
+        __syncthreads();
+    }
+    long long run_mx = threadIdx.x ? s_mx[threadIdx.x - 1] : -1;
+    long long run_sum = threadIdx.x ? s_sum[threadIdx.x - 1] : 0;
+    for (size_t i = lo; i < hi; i++) {
+        prev_nl[i] = run_mx;
+        nl_before[i] = run_sum;
+        run_mx = max(run_mx, blk_last_nl[i]);
+        run_sum += blk_nl_count[i];
+    }
+    if (threadIdx.x == 1023) { prev_nl[nb] = s_mx[1023]; nl_before[nb] = s_sum[1023]; }
+}
+
+// Classify the block's bytes.  Thread t owns bytes [bstart + 16t, +16).  The line state entering the
+// thread's chunk (start of the current line, its index) comes from a block-wide exclusive scan of
+// (last newline position, newline count) seeded with the per-block prefixes.  A record "event" is the
+// newline that ends a name line: there the name span and the sequence offset of the record are known.
+template <bool FASTQ, bool COUNT>
+__global__ void __launch_bounds__(FX_THREADS) fx_emit_kernel(const uint8_t *__restrict__ text, size_t n,
+                                                             const long long *__restrict__ prev_nl_blk,
+                                                             const long long *__restrict__ nl_before_blk,
+                                                             uint32_t *__restrict__ blk_kept, uint32_t *__restrict__ blk_recs,
+                                                             const long long *__restrict__ kept_before_blk,
+                                                             const long long *__restrict__ recs_before_blk, FxOut out,
+                                                             FxInfo *__restrict__ info)
+{
+    __shared__ long long s_a[FX_THREADS / 32];
+    __shared__ uint32_t s_b[FX_THREADS / 32], s_c[FX_THREADS / 32];
+    const size_t pos = (size_t)blockIdx.x * FX_BLK + 16u * threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (pos < n) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + pos));
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    }
+    // --- phase A: newline summary of my chunk, block-exclusive scan (max position, count) ---
+    uint32_t nl_mask = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        if (pos + j < n && byte_of(w, j) == '\n') nl_mask |= 1u << j;
+    const long long my_last = nl_mask ? (long long)pos + (31 - __clz(nl_mask)) : -1;
+    const uint32_t my_cnt = __popc(nl_mask);
+    long long inc_last = my_last;
+    uint32_t inc_cnt = my_cnt;
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long a = __shfl_up_sync(0xffffffffu, inc_last, d);
+        const uint32_t b = __shfl_up_sync(0xffffffffu, inc_cnt, d);
+        if (lane >= (uint32_t)d) { inc_last = max(inc_last, a); inc_cnt += b; }
+    }
+    if (lane == 31) { s_a[wid] = inc_last; s_b[wid] = inc_cnt; }
+    __syncthreads();
+    long long prev_nl = prev_nl_blk[blockIdx.x];
+    long long nl_before = nl_before_blk[blockIdx.x];
+    for (uint32_t k = 0; k < wid; k++) { prev_nl = max(prev_nl, s_a[k]); nl_before += s_b[k]; }
+    {
+        const long long a = __shfl_up_sync(0xffffffffu, inc_last, 1);
+        const uint32_t b = __shfl_up_sync(0xffffffffu, inc_cnt, 1);
+        if (lane) { prev_nl = max(prev_nl, a); nl_before += b; }
+    }
+    __syncthreads();   // s_b is reused below
+    // --- phase B: walk my 16 bytes with the line state ---
+    long long line_start = prev_nl + 1;
+    long long line_no = nl_before;
+    bool header_line = !FASTQ && pos < n && text[line_start] == '>';   // FASTA: line starts with '>'
+    uint32_t kept_mask = 0, ev_mask = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t c = byte_of(w, j);
+        if ((nl_mask >> j) & 1u) {
+            const bool name_line = FASTQ ? ((line_no & 3) == 0) : header_line;
+            if (name_line) ev_mask |= 1u << j;
+            line_start = (long long)(pos + j) + 1;
+            line_no++;
+            if (!FASTQ) header_line = (size_t)line_start < n && text[line_start] == '>';
+        } else if (pos + j < n) {
+            const bool seq_line = FASTQ ? ((line_no & 3) == 1) : !header_line;
+            if (seq_line && !is_ws(c)) kept_mask |= 1u << j;
+        }
+    }
+    const uint32_t my_kept = __popc(kept_mask), my_ev = __popc(ev_mask);
+    uint32_t inc_k = my_kept, inc_e = my_ev;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, inc_k, d), b = __shfl_up_sync(0xffffffffu, inc_e, d);
+        if (lane >= (uint32_t)d) { inc_k += a; inc_e += b; }
+    }
+    if (lane == 31) { s_b[wid] = inc_k; s_c[wid] = inc_e; }
+    __syncthreads();
+    if (COUNT) {
+        if (threadIdx.x == 0) {
+            uint32_t tk = 0, te = 0;
+            for (int k = 0; k < FX_THREADS / 32; k++) { tk += s_b[k]; te += s_c[k]; }
+            blk_kept[blockIdx.x] = tk;
+            blk_recs[blockIdx.x] = te;
+        }
+        return;
+    }
+    long long kept_run = kept_before_blk[blockIdx.x] + inc_k - my_kept;
+    long long rec_run = recs_before_blk[blockIdx.x] + inc_e - my_ev;
+    for (uint32_t k = 0; k < wid; k++) { kept_run += s_b[k]; rec_run += s_c[k]; }
+    // --- scatter ---
+    line_start = prev_nl + 1;
+    line_no = nl_before;
+    uint8_t *dst = out.residues + kept_run;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const long long p = (long long)(pos + j);
+        if ((kept_mask >> j) & 1u) { *dst++ = (uint8_t)byte_of(w, j); kept_run++; }
+        if ((nl_mask >> j) & 1u) {
+            long long le = p;                                   // line end, '\r' of a CRLF break dropped
+            if (le > line_start && text[le - 1] == '\r') le--;
+            if ((ev_mask >> j) & 1u) {
+                const long long r = rec_run++;
+                if (r < out.max_records) {
+                    out.name_start[r] = line_start + 1;         // skip '>' / '@'
+                    out.name_len[r] = (int)(le - line_start - 1 > 0 ? le - line_start - 1 : 0);
+                    out.offsets[r] = kept_run;                  // nothing of a name line is ever kept
+                    out.rec_start[r] = line_start;
+                    if (text[line_start] != (FASTQ ? '@' : '>')) info->status = FX_BAD_MARKER;
+                } else {
+                    info->status = FX_TOO_MANY_RECORDS;
+                }
+            } else if (FASTQ) {
+                const long long kind = line_no & 3;
+                const long long r = rec_run - 1;                // the record this line belongs to
+                if (kind == 2 && text[line_start] != '+') info->status = FX_BAD_MARKER;
+                if (kind == 3 && r >= 0 && r < out.max_records) {
+                    out.qual_start[r] = line_start;
+                    out.qual_len[r] = (int)(le - line_start);
+                }
+            }
+            line_start = p + 1;
+            line_no++;
+        }
+    }
+}
+
+// Record count, closing offset and consumed bytes.  FASTA: a record is complete when the next record's
+// name line has been seen, or at the end of the final chunk.  FASTQ: when its 4th line has ended.
+__global__ void fx_finish_kernel(const long long *__restrict__ kept_prefix, const long long *__restrict__ rec_prefix,
+                                 const long long *__restrict__ nl_before, const long long *__restrict__ prev_nl, size_t nb,
+                                 size_t n, int fastq, int is_final, FxOut out, FxInfo *__restrict__ info)
+{
+    long long n_ev = rec_prefix[nb];
+    if (n_ev > out.max_records) { n_ev = out.max_records; info->status = FX_TOO_MANY_RECORDS; }
+    const long long kept = kept_prefix[nb];
+    long long nrec, consumed;
+    if (fastq) {
+        const long long lines = nl_before[nb];
+        nrec = lines / 4 < n_ev ? lines / 4 : n_ev;
+        if (nrec == n_ev) {          // every record whose name line ended is complete
+            out.offsets[nrec] = kept;
+            consumed = is_final ? (long long)n : prev_nl[nb] + 1;   // up to the last line break
+        } else {
+            consumed = out.rec_start[nrec];   // offsets[nrec] was written by the incomplete record's event
+        }
+    } else if (is_final) {
+        nrec = n_ev;
+        out.offsets[nrec] = kept;
+        consumed = (long long)n;
+    } else {
+        nrec = n_ev > 0 ? n_ev - 1 : 0;       // the last record may continue in the next chunk
+        consumed = n_ev > 0 ? out.rec_start[nrec] : 0;
+        if (n_ev == 0) out.offsets[0] = 0;
+    }
+    if (nrec == 0) out.offsets[0] = 0;
+    info->n_records = nrec;
+    info->n_residues = out.offsets[nrec];
+    info->consumed = consumed;
+}
+
+// ------------------------------------------------------------------------------------------- formatter
+
+__device__ __forceinline__ uint32_t fmt_name_field_len(const FmtCfg &c, bool empty, int name_len)
+{
+    uint32_t len = (c.label_len >= 0 ? (uint32_t)c.label_len + 1u : 0u) + (uint32_t)name_len;
+    for (int k = 0; k < c.n_algos; k++) len += (empty ? 0u : 2u * (uint32_t)c.dsize[k]) + 1u;
+    return len;
+}
+
+__global__ void fmt_len_kernel(FmtCfg c, FxOut rec, size_t n, uint32_t *__restrict__ out_len,
+                               unsigned long long *__restrict__ n_empty)
+{
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const long long slen = rec.offsets[r + 1] - rec.offsets[r];
+    const bool empty = slen == 0;
+    uint32_t len = fmt_name_field_len(c, empty, rec.name_len[r]) + 1u;   // name + '\n'
+    if (!c.headers_only) {
+        len += 1u + (uint32_t)slen + 1u;                                  // marker, sequence, '\n'
+        if (c.fastq && rec.qual_len[r] > 0) len += 2u + (uint32_t)rec.qual_len[r] + 1u;   // "+\n" quality '\n'
+    }
+    out_len[r] = len;
+    if (empty) atomicAdd(n_empty, 1ULL);
+}
+
+// One warp per record; lane j writes output bytes j, j+32, ...  Segments in order:
+// [marker] [label ';'] [hex(h_k) ';']* name '\n' [sequence '\n' ['+' '\n' quality '\n']]
+__global__ void __launch_bounds__(256) fmt_write_kernel(FmtCfg c, FxOut rec, size_t n, const uint8_t *__restrict__ text,
+                                                        const long long *__restrict__ out_off, uint8_t *__restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        const long long s0 = rec.offsets[r], slen = rec.offsets[r + 1] - s0;
+        const bool empty = slen == 0;
+        const int name_len = rec.name_len[r];
+        const bool fq = c.fastq && rec.qual_len[r] > 0;   // record.Format: FASTQ iff quality present
+        const uint32_t b_marker = c.headers_only ? 0u : 1u;
+        const uint32_t b_label = b_marker + (c.label_len >= 0 ? (uint32_t)c.label_len + 1u : 0u);
+        uint32_t b_hash = b_label;
+        for (int k = 0; k < c.n_algos; k++) b_hash += (empty ? 0u : 2u * (uint32_t)c.dsize[k]) + 1u;
+        const uint32_t b_name = b_hash + (uint32_t)name_len + 1u;
+        const uint32_t b_seq = c.headers_only ? b_name : b_name + (uint32_t)slen + 1u;
+        const uint32_t b_end = (uint32_t)(out_off[r + 1] - out_off[r]);
+        uint8_t *o = out + out_off[r];
+        for (uint32_t j = lane; j < b_end; j += 32) {
+            uint8_t ch;
+            if (j < b_marker) {
+                ch = fq ? '@' : '>';
+            } else if (j < b_label) {
+                const uint32_t q = j - b_marker;
+                ch = q < (uint32_t)c.label_len ? c.label[q] : ';';
+            } else if (j < b_hash) {
+                uint32_t q = j - b_label;
+                ch = ';';
+                for (int k = 0; k < c.n_algos; k++) {
+                    const uint32_t fl = empty ? 0u : 2u * (uint32_t)c.dsize[k];
+                    if (q < fl) {
+                        const uint8_t byte = c.digests[k][r * (size_t)c.dsize[k] + (q >> 1)];
+                        const uint32_t nib = (q & 1u) ? (byte & 15u) : (byte >> 4);
+                        ch = (uint8_t)(nib < 10 ? '0' + nib : 'a' + nib - 10);
+                        break;
+                    }
+                    if (q == fl) break;   // the ';' after this hash
+                    q -= fl + 1u;
+                }
+            } else if (j < b_name) {
+                const uint32_t q = j - b_hash;
+                ch = q < (uint32_t)name_len ? text[rec.name_start[r] + q] : '\n';
+            } else if (j < b_seq) {
+                const uint32_t q = j - b_name;
+                if (q < (uint32_t)slen) {
+                    uint32_t b = rec.residues[s0 + q];
+                    if (c.upper && b - 'a' < 26u) b -= 32u;      // seqhasher.go:249-252
+                    ch = (uint8_t)b;
+                } else {
+                    ch = '\n';
+                }
+            } else {
+                const uint32_t q = j - b_seq;   // "+\n" quality "\n"
+                if (q == 0) ch = '+';
+                else if (q == 1) ch = '\n';
+                else if (q - 2 < (uint32_t)rec.qual_len[r]) ch = text[rec.qual_start[r] + (q - 2)];
+                else ch = '\n';
+            }
+            o[j] = ch;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- launchers
+
+cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, cudaStream_t st);   // kernels.cu
+
+size_t fx_scratch_bytes(size_t n_bytes)
+{
+    const size_t nb = n_bytes / FX_BLK + 1;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    // last_nl, nl_count, prev_nl, nl_before, blk_kept, blk_recs, kept_prefix, rec_prefix
+    return up(nb * 8) + up(nb * 4) + 2 * up((nb + 1) * 8) + 2 * up(nb * 4) + 2 * up((nb + 1) * 8);
+}
+
+cudaError_t launch_fx_parse(const uint8_t *text, size_t n, bool fastq, bool is_final, FxOut out, FxInfo *info,
+                            void *scratch, cudaStream_t st)
+{
+    const size_t nb = n / FX_BLK + 1;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    uint8_t *p = static_cast<uint8_t *>(scratch);
+    long long *last_nl = reinterpret_cast<long long *>(p); p += up(nb * 8);
+    uint32_t *nl_count = reinterpret_cast<uint32_t *>(p); p += up(nb * 4);
+    long long *prev_nl = reinterpret_cast<long long *>(p); p += up((nb + 1) * 8);
+    long long *nl_before = reinterpret_cast<long long *>(p); p += up((nb + 1) * 8);
+    uint32_t *blk_kept = reinterpret_cast<uint32_t *>(p); p += up(nb * 4);
+    uint32_t *blk_recs = reinterpret_cast<uint32_t *>(p); p += up(nb * 4);
+    long long *kept_prefix = reinterpret_cast<long long *>(p); p += up((nb + 1) * 8);
+    long long *rec_prefix = reinterpret_cast<long long *>(p);
+    cudaError_t e = cudaMemsetAsync(info, 0, sizeof(FxInfo), st);
+    if (e != cudaSuccess) return e;
+    if (fastq && (e = cudaMemsetAsync(out.qual_len, 0, (size_t)out.max_records * sizeof(int), st)) != cudaSuccess) return e;
+    fx_lines_kernel<<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, last_nl, nl_count);
+    fx_scan_kernel<<<1, 1024, 0, st>>>(last_nl, nl_count, nb, prev_nl, nl_before);
+    if (fastq) fx_emit_kernel<true, true><<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, prev_nl, nl_before, blk_kept, blk_recs, nullptr, nullptr, out, info);
+    else fx_emit_kernel<false, true><<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, prev_nl, nl_before, blk_kept, blk_recs, nullptr, nullptr, out, info);
+    g_launches += 3;
+    if ((e = scan_counts(blk_kept, nb, reinterpret_cast<int64_t *>(kept_prefix), st)) != cudaSuccess) return e;
+    if ((e = scan_counts(blk_recs, nb, reinterpret_cast<int64_t *>(rec_prefix), st)) != cudaSuccess) return e;
+    if (fastq) fx_emit_kernel<true, false><<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, prev_nl, nl_before, nullptr, nullptr, kept_prefix, rec_prefix, out, info);
+    else fx_emit_kernel<false, false><<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, prev_nl, nl_before, nullptr, nullptr, kept_prefix, rec_prefix, out, info);
+    fx_finish_kernel<<<1, 1, 0, st>>>(kept_prefix, rec_prefix, nl_before, prev_nl, nb, n, fastq ? 1 : 0, is_final ? 1 : 0, out, info);
+    g_launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fx_format(const FmtCfg &cfg, const FxOut &rec, size_t n, const uint8_t *text, uint32_t *out_len,
+                             long long *out_off, uint8_t *out, FxInfo *info, bool lengths_only, cudaStream_t st)
+{
+    if (lengths_only) {
+        if (n) fmt_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cfg, rec, n, out_len,
+                                                                         reinterpret_cast<unsigned long long *>(&info->n_empty));
+        g_launches++;
+        return scan_counts(out_len, n, reinterpret_cast<int64_t *>(out_off), st);
+    }
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n + 7) / 8;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    fmt_write_kernel<<<(unsigned)blocks, 256, 0, st>>>(cfg, rec, n, text, out_off, out);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace shb

@@ -1,0 +1,50 @@
+// parse.cuh — record splitter / formatter interface (internal to libseqhash_b200).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace shb {
+
+constexpr uint32_t FX_BLK = 4096;
+enum : long long { FX_OK = 0, FX_BAD_MARKER = 1, FX_TOO_MANY_RECORDS = 2 };
+
+struct FxInfo {            // device-side result block
+    long long n_records;   // complete records
+    long long n_residues;  // residue bytes of those records (= offsets[n_records])
+    long long status;      // FX_*
+    long long consumed;    // bytes of the text covered by the complete records
+    long long n_empty;     // records whose sequence is empty (formatter)
+    long long reserved;
+};
+
+struct FxOut {
+    uint8_t *residues;       // compacted (whitespace-free) sequence bytes
+    long long *offsets;      // max_records + 1
+    long long *name_start;   // first byte of the record name in the text
+    int *name_len;
+    long long *qual_start;   // FASTQ: quality line
+    int *qual_len;
+    long long *rec_start;    // line start of the record's name line
+    long long max_records;
+};
+
+struct FmtCfg {
+    const uint8_t *label;    // device copy of the file label
+    int label_len;           // -1: no file name field
+    int n_algos;
+    int dsize[N_ALGOS];
+    const uint8_t *digests[N_ALGOS];
+    int headers_only, fastq, upper;
+};
+
+size_t fx_scratch_bytes(size_t n_bytes);
+cudaError_t launch_fx_parse(const uint8_t *text, size_t n, bool fastq, bool is_final, FxOut out, FxInfo *info,
+                            void *scratch, cudaStream_t st);
+// lengths_only: per-record output lengths into out_len + exclusive scan into out_off (n+1); else write the text
+cudaError_t launch_fx_format(const FmtCfg &cfg, const FxOut &rec, size_t n, const uint8_t *text, uint32_t *out_len,
+                             long long *out_off, uint8_t *out, FxInfo *info, bool lengths_only, cudaStream_t st);
+
+}  // namespace shb

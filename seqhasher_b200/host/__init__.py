@@ -3,4 +3,4 @@ process_sequences, run — same names, argument meaning and error behaviour, wit
 strip/upper/hash statements (seqhasher.go:246-259) replaced by batched calls into libseqhash_b200.so."""
 from .cli import Config, main, parse_flags, run  # noqa: F401
 from .hasher import GpuHasher, get_hash_func, is_valid_hash_type, SUPPORTED_HASH_TYPES  # noqa: F401
-from .process import process_sequences  # noqa: F401
+from .process import process_sequences, process_sequences_gpu  # noqa: F401

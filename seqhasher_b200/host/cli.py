@@ -109,7 +109,7 @@ def print_usage(w, prog: str = "seqhasher") -> None:
 def run(argv: list[str], w=None, stdin=None) -> None:
     """run (seqhasher.go:62-99).  w is a text writer for version/usage and a binary sink for records
     (sys.stdout by default).  Raises RuntimeError / ValueError with the reference's error texts."""
-    from .process import process_sequences
+    from .process import process_sequences_gpu as process_sequences   # whole record loop on the GPU
     w = w or sys.stdout
     cfg = parse_flags(argv)
     if cfg.show_version:

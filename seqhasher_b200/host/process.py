@@ -63,3 +63,87 @@ def process_sequences(input_stream, output_stream, cfg, hasher: GpuHasher | None
         flush(batch)
     finally:
         out.flush()
+
+
+def process_sequences_gpu(input_stream, output_stream, cfg, textproc=None, chunk_bytes: int = 64 << 20, log=None) -> None:
+    """processSequences with the WHOLE record loop on the GPU (shb_textproc): the host only decompresses and
+    moves bytes.  Same observable behaviour as process_sequences (output text, error texts, one stderr line
+    per empty record and hash type)."""
+    import sys
+
+    from .. import binding as B
+    from .fastx import ERR_INVALID, open_maybe_compressed
+    from .hasher import EMPTY_MSG, _algo_ids
+    log = log or sys.stderr
+    label = cfg.input_file_name
+    no_file_name = cfg.no_file_name
+    if cfg.name_override != "":
+        label = cfg.name_override
+    elif label == "-":
+        no_file_name = True   # seqhasher.go:217-219
+    own = textproc is None
+    if len(cfg.hash_types) > 12:
+        # the GPU formatter carries at most 12 hash fields; longer lists take the host-side loop
+        return process_sequences(input_stream, output_stream, cfg)
+    tp = textproc or B.TextProc(chunk_bytes)
+    ids = _algo_ids(cfg.hash_types)
+    flags = 0 if cfg.case_sensitive else B.FLAG_UPPER
+    f = open_maybe_compressed(input_stream)
+    try:
+        fill = 0          # bytes currently in tp.input
+        fmt = 0
+        eof = False
+        while True:
+            while not eof and fill < tp.capacity:
+                chunk = f.read(tp.capacity - fill)
+                if not chunk:
+                    eof = True
+                    break
+                tp.input[fill: fill + len(chunk)] = memoryview(chunk)
+                fill += len(chunk)
+            if fmt == 0:
+                # sniff: skip leading blank space, first byte decides (fastx.NewReaderFromIO, seqhasher.go:221)
+                head = bytes(tp.input[:fill])
+                skip = len(head) - len(head.lstrip())
+                if skip == fill:
+                    if eof:
+                        return          # empty input: no records
+                    fill = 0
+                    continue
+                first = head[skip: skip + 1]
+                if first == b">":
+                    fmt = B.FORMAT_FASTA
+                elif first == b"@":
+                    fmt = B.FORMAT_FASTQ
+                else:
+                    raise RuntimeError(f"Failed to create reader: {ERR_INVALID}")
+                if skip:
+                    tp.input[: fill - skip] = tp.input[skip:fill].copy()
+                    fill -= skip
+            if eof:
+                # trailing blank lines are not records
+                tail = bytes(tp.input[max(0, fill - 4096): fill])
+                fill -= len(tail) - len(tail.rstrip())
+                if fill == 0:
+                    return
+            try:
+                out, consumed, nrec, nempty = tp.run(fill, fmt, eof, ids, flags, cfg.headers_only,
+                                                     None if no_file_name else label.encode())
+            except B.SeqhashError as e:
+                if ERR_INVALID in str(e):
+                    raise RuntimeError(f"Error reading record: {ERR_INVALID}") from None
+                raise
+            for _ in range(nempty * len(ids)):
+                print(EMPTY_MSG, file=log)
+            output_stream.write(out)
+            if eof:
+                return
+            if consumed == 0:
+                raise RuntimeError("Error reading record: record larger than the GPU text buffer")
+            rest = fill - consumed
+            if rest:
+                tp.input[:rest] = tp.input[consumed:fill].copy()
+            fill = rest
+    finally:
+        if own:
+            tp.close()

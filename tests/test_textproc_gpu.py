@@ -1,0 +1,167 @@
+"""The whole record loop on the GPU (shb_textproc: split -> strip -> upper -> hash -> header rewrite -> format)
+against a CPU expectation built from the host reader (bio semantics) + the oracle, on the reference's fixtures
+and on synthetic multi-line FASTA / 4-line FASTQ that span many 4 KiB scan blocks and several chunks."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixtures")
+
+
+@pytest.fixture(scope="module")
+def H():
+    from seqhasher_b200 import host
+    return host
+
+
+def expected(oracle, data: bytes, cfg) -> bytes:
+    """seqhasher.go:210-286 on the CPU: host reader + oracle hashes + the reference's formatting."""
+    from seqhasher_b200.host.fastx import read_records
+    label, nofile = cfg.input_file_name, cfg.no_file_name
+    if cfg.name_override:
+        label = cfg.name_override
+    elif label == "-":
+        nofile = True
+    flags = 2 | (0 if cfg.case_sensitive else 1)
+    out = io.BytesIO()
+    for rec in read_records(io.BytesIO(data)):
+        seq = oracle.normalise(rec.seq, flags)
+        hashes = ";".join(oracle.get_hash_func(t)(seq) for t in cfg.hash_types).encode()
+        parts = ([] if nofile else [label.encode()]) + ([hashes] if cfg.hash_types else []) + [rec.name]
+        name = b";".join(parts)
+        if cfg.headers_only:
+            out.write(name + b"\n")
+        elif rec.qual:
+            out.write(b"@" + name + b"\n" + seq + b"\n+\n" + rec.qual + b"\n")
+        else:
+            out.write(b">" + name + b"\n" + seq + b"\n")
+    return out.getvalue()
+
+
+def run_gpu(H, data: bytes, cfg, chunk=1 << 20) -> bytes:
+    from seqhasher_b200 import binding as B
+    tp = B.TextProc(chunk)
+    try:
+        out = io.BytesIO()
+        H.process_sequences_gpu(io.BytesIO(data), out, cfg, textproc=tp, log=io.StringIO())
+        return out.getvalue()
+    finally:
+        tp.close()
+
+
+CFGS = [
+    dict(hash_types=["sha1"], input_file_name="test.fasta"),
+    dict(hash_types=["md5"], headers_only=True, no_file_name=True, input_file_name="x"),
+    dict(hash_types=["sha1", "xxhash", "nthash"], case_sensitive=True, input_file_name="-"),
+    dict(hash_types=["xxh3", "blake3", "k12", "rapidhash32"], name_override="lbl", input_file_name="in.fa", headers_only=True),
+]
+
+
+@pytest.mark.parametrize("fixture", ["test.fasta", "test2.fasta", "test3.fastq", "seqs_with_spaces.fasta",
+                                     "problematic_sequences.fasta", "test.fasta.gz", "test2.fasta.zst", "test.fasta.xz",
+                                     "test2.fasta.bz2"])
+def test_fixtures(H, oracle, fixture):
+    data = open(os.path.join(FIX, fixture), "rb").read()
+    import gzip, bz2, lzma
+    for kw in CFGS:
+        cfg = H.Config(**kw)
+        got = run_gpu(H, data, cfg)
+        plain = b"".join(_plain(data))
+        assert got == expected(oracle, plain, cfg), (fixture, kw)
+
+
+def _plain(data):
+    from seqhasher_b200.host.fastx import open_maybe_compressed
+    yield open_maybe_compressed(io.BytesIO(data)).read()
+
+
+def synth_fasta(n, seed, crlf=False, wrap=60):
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTacgtNRY", dtype=np.uint8)
+    eol = b"\r\n" if crlf else b"\n"
+    out = []
+    for i in range(n):
+        L = int(rng.integers(0, 3000)) if i % 37 else 0
+        seq = rng.choice(alphabet, size=L).tobytes()
+        name = f"seq_{i} desc with spaces len={L}".encode() if i % 5 else b"s%d" % i
+        out.append(b">" + name + eol)
+        w = wrap if i % 3 else 10 ** 9
+        for k in range(0, L, w):
+            line = seq[k:k + w]
+            if i % 11 == 0 and len(line) > 4:
+                line = line[:2] + b" \t" + line[2:]     # interior blanks: stripped by seqhasher.go:246
+            out.append(line + eol)
+        if i % 13 == 0:
+            out.append(eol)                              # blank line inside the file
+    return b"".join(out)
+
+
+def synth_fastq(n, seed, crlf=False):
+    rng = np.random.default_rng(seed)
+    eol = b"\r\n" if crlf else b"\n"
+    qa = np.frombuffer(bytes(range(33, 74)), dtype=np.uint8)    # includes '@' (64) and '+' (43)
+    out = []
+    for i in range(n):
+        L = int(rng.integers(1, 400))
+        seq = rng.choice(np.frombuffer(b"ACGTNacgt", dtype=np.uint8), size=L).tobytes()
+        qual = rng.choice(qa, size=L).tobytes()
+        if i % 7 == 0:
+            qual = b"@" + qual[1:]
+        if i % 9 == 0:
+            qual = b"+" + qual[1:]
+        out.append(b"@read_%d some/1" % i + eol + seq + eol + b"+" + eol + qual + eol)
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_multiline_fasta_chunked(H, oracle, crlf):
+    data = b"\n\n" + synth_fasta(900, 3, crlf) + b"\n\n"
+    for kw in (CFGS[0], CFGS[1], dict(hash_types=["xxh3", "murmur3"], input_file_name="f.fa")):
+        cfg = H.Config(**kw)
+        want = expected(oracle, data, cfg)
+        assert run_gpu(H, data, cfg, chunk=1 << 22) == want           # one chunk
+        assert run_gpu(H, data, cfg, chunk=40_000) == want            # many chunks, records carried over
+    # no trailing line break at EOF, header-only last record
+    data2 = synth_fasta(50, 4) + b">last_empty"
+    cfg = H.Config(hash_types=["sha1"], input_file_name="z")
+    assert run_gpu(H, data2, cfg, chunk=9000) == expected(oracle, data2, cfg)
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_fastq_chunked(H, oracle, crlf):
+    data = synth_fastq(3000, 8, crlf)
+    for kw in (dict(hash_types=["sha1"], input_file_name="-"), dict(hash_types=["xxhash", "xxh3", "murmur3"], headers_only=True,
+                                                                       input_file_name="r.fq")):
+        cfg = H.Config(**kw)
+        want = expected(oracle, data, cfg)
+        assert run_gpu(H, data, cfg, chunk=1 << 22) == want
+        assert run_gpu(H, data, cfg, chunk=30_000) == want
+    nolf = data.rstrip()                                               # last quality line without a line break
+    cfg = H.Config(hash_types=["md5"], input_file_name="q")
+    assert run_gpu(H, nolf, cfg, chunk=50_000) == expected(oracle, nolf, cfg)
+
+
+def test_errors_and_empty(H):
+    cfg = H.Config(hash_types=["sha1"], input_file_name="x")
+    with pytest.raises(RuntimeError) as e:
+        run_gpu(H, b"this is not a sequence file\n", cfg)
+    assert str(e.value) == "Failed to create reader: fastx: invalid FASTA/Q format"   # seqhasher_test.go:795
+    assert run_gpu(H, b"", cfg) == b"" and run_gpu(H, b"\n \n", cfg) == b""
+    with pytest.raises(RuntimeError):
+        run_gpu(H, b"@r1\nACGT\nX\nIIII\n", cfg)                       # third line must start with '+'
+
+
+def test_empty_sequence_log_lines(H):
+    from seqhasher_b200 import binding as B
+    tp = B.TextProc(1 << 16)
+    log = io.StringIO()
+    out = io.BytesIO()
+    H.process_sequences_gpu(io.BytesIO(b">a\n\n>b\nAC\n>c\n"), out, H.Config(hash_types=["sha1", "md5"], input_file_name="f"),
+                            textproc=tp, log=log)
+    tp.close()
+    assert out.getvalue().startswith(b">f;;;a\n\n>f;") and out.getvalue().endswith(b">f;;;c\n\n")
+    assert log.getvalue().count("Empty DNA sequence") == 4            # 2 empty records x 2 hash types

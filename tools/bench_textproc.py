@@ -1,0 +1,63 @@
+"""End-to-end throughput of the whole record loop on the GPU (shb_textproc): FASTA/FASTQ TEXT in pinned host
+memory -> output text in host memory (H2D, split, strip, upper, hash, header rewrite, format, D2H all inside
+the timed region).  usage: python tools/bench_textproc.py [--records 4000000] [--len 250] [--fastq]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from seqhasher_b200 import binding as B  # noqa: E402
+
+
+def make_text(n, L, fastq):
+    from synth import synth_bytes
+    base = 20000
+    seq = synth_bytes(base * L, 0xC2, 50).reshape(base, L)
+    rows = []
+    for i in range(base):
+        if fastq:
+            rows.append(b"@read_%07d\n" % i + seq[i].tobytes() + b"\n+\n" + b"I" * L + b"\n")
+        else:
+            rows.append(b">seq_%07d\n" % i + seq[i].tobytes() + b"\n")
+    block = b"".join(rows)
+    reps = (n + base - 1) // base
+    return block * reps, base * reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--records", type=int, default=4_000_000)
+    ap.add_argument("--len", type=int, default=250)
+    ap.add_argument("--fastq", action="store_true")
+    ap.add_argument("--hash", default="sha1")
+    ap.add_argument("--full", action="store_true", help="full-record output instead of --headersonly")
+    ap.add_argument("--steps", type=int, default=5)
+    a = ap.parse_args()
+    B.init(1)
+    text, n = make_text(a.records, a.len, a.fastq)
+    tp = B.TextProc(len(text) + 1024)
+    tp.input[: len(text)] = np.frombuffer(text, dtype=np.uint8)
+    ids = [B.algo_id(h) for h in a.hash.split(",")]
+    fmt = B.FORMAT_FASTQ if a.fastq else B.FORMAT_FASTA
+    for _ in range(2):
+        out, consumed, nrec, _ = tp.run(len(text), fmt, True, ids, B.FLAG_UPPER, not a.full, b"big.fasta")
+    assert nrec == n and consumed == len(text)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        out, consumed, nrec, _ = tp.run(len(text), fmt, True, ids, B.FLAG_UPPER, not a.full, b"big.fasta")
+    dt = (time.perf_counter() - t0) / a.steps
+    print(json.dumps({"what": "shb_textproc end to end (host text -> host output)", "records": n, "read_len": a.len,
+                      "format": "fastq" if a.fastq else "fasta", "hash": a.hash, "headers_only": not a.full,
+                      "text_bytes": len(text), "out_bytes": len(out), "ms_per_step": dt * 1e3, "seqs_per_s": n / dt,
+                      "text_gbps": len(text) / dt / 1e9, "first_line": out[:80].split(b"\n")[0].decode()}))
+    tp.close()
+
+
+if __name__ == "__main__":
+    main()
