@@ -146,6 +146,8 @@ const uint8_t *shb_textproc_output(shb_textproc *t, size_t *out_bytes);
 size_t shb_textproc_consumed(shb_textproc *t);
 size_t shb_textproc_records(shb_textproc *t);
 size_t shb_textproc_empty_records(shb_textproc *t);
+/* device time of the last run, ms: H2D copy, record split, hashes, formatting (incl. its host syncs), D2H copy */
+void shb_textproc_last_ms(shb_textproc *t, float *ms5);
 
 /* ---- measurement helpers (not part of the hashing path) ---- */
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "shb_out_residues", "shb_scratch_bytes", "shb_hash_device", "shb_launch_count", "shb_synth_fill",
     "shb_probe_int_peak", "shb_probe_last_checksum", "shb_textproc_create", "shb_textproc_destroy",
     "shb_textproc_input", "shb_textproc_capacity", "shb_textproc_run", "shb_textproc_output", "shb_textproc_consumed",
-    "shb_textproc_records", "shb_textproc_empty_records",
+    "shb_textproc_records", "shb_textproc_empty_records", "shb_textproc_last_ms",
 ]
 FORMAT_FASTA = 1
 FORMAT_FASTQ = 2
@@ -87,6 +87,7 @@ def lib() -> ctypes.CDLL:
                                    c.c_char_p]
     L.shb_textproc_run.restype = c.c_int
     L.shb_textproc_output.argtypes = [c.c_void_p, c.POINTER(c.c_size_t)]; L.shb_textproc_output.restype = c.c_void_p
+    L.shb_textproc_last_ms.argtypes = [c.c_void_p, c.POINTER(c.c_float)]; L.shb_textproc_last_ms.restype = None
     for nm in ("shb_textproc_consumed", "shb_textproc_records", "shb_textproc_empty_records"):
         getattr(L, nm).argtypes = [c.c_void_p]; getattr(L, nm).restype = c.c_size_t
     _lib = L
@@ -275,5 +276,11 @@ class TextProc:
                                   1 if headers_only else 0, label), "shb_textproc_run")
         nb = ctypes.c_size_t(0)
         p = L.shb_textproc_output(self._h, ctypes.byref(nb))
-        out = ctypes.string_at(p, nb.value) if nb.value else b""
+        # zero-copy view of the pinned output buffer (valid until the next run)
+        out = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(nb.value,)) if nb.value else np.zeros(0, np.uint8)
         return out, L.shb_textproc_consumed(self._h), L.shb_textproc_records(self._h), L.shb_textproc_empty_records(self._h)
+
+    def last_ms(self) -> dict:
+        arr = (ctypes.c_float * 5)()
+        lib().shb_textproc_last_ms(self._h, arr)
+        return dict(zip(["h2d", "split", "hash", "format", "d2h"], [float(x) for x in arr]))

@@ -40,7 +40,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // scratch layout of the normalise pre-pass inside one allocation
 struct ScratchLayout {
-    size_t res_off, offs_off, counts_off, prefix_off, b3_off, total;
+    size_t res_off, offs_off, counts_off, prefix_off, scan_off, b3_off, total;
     ScratchLayout(size_t total_bytes, size_t n)
     {
         const size_t nb = shb::norm_blocks(total_bytes);
@@ -48,7 +48,8 @@ struct ScratchLayout {
         offs_off = align_up(total_bytes + 32, 256);
         counts_off = offs_off + align_up((n + 1) * sizeof(int64_t), 256);
         prefix_off = counts_off + align_up(nb * sizeof(uint32_t), 256);
-        b3_off = prefix_off + align_up((nb + 1) * sizeof(int64_t), 256);   // BLAKE3 long path: counts, bases, CVs
+        scan_off = prefix_off + align_up((nb + 1) * sizeof(int64_t), 256);
+        b3_off = scan_off + align_up(shb::scan_tmp_bytes(nb), 256);          // BLAKE3 long path: counts, bases, CVs
         total = b3_off + shb::b3_long_scratch_bytes(total_bytes, n);
     }
 };
@@ -80,7 +81,8 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         int64_t *o_offs = reinterpret_cast<int64_t *>(base + L.offs_off);
         CU(shb::launch_normalise(d_res, d_offs, n, total_bytes, strip, upper,
                                  reinterpret_cast<uint32_t *>(base + L.counts_off),
-                                 reinterpret_cast<int64_t *>(base + L.prefix_off), o_res, o_offs, d_out_len, st));
+                                 reinterpret_cast<int64_t *>(base + L.prefix_off), o_res, o_offs, d_out_len,
+                                 base + L.scan_off, st));
         res = o_res;
         offs = o_offs;
         fused_upper = false;   // already applied while compacting
@@ -114,7 +116,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
                                      reinterpret_cast<int64_t *>(static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).prefix_off),
                                      static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).res_off,
                                      reinterpret_cast<int64_t *>(static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).offs_off),
-                                     d_out_len, st));
+                                     d_out_len, static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).scan_off, st));
     } else {
         // mean >= 2 KiB: the hashes with parallelism inside a record leave the thread-per-record path
         const bool long_mode = n && mean >= 2048;
@@ -122,6 +124,8 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
             if (!(want >> a & 1u)) continue;
             if (long_mode && a == SHB_NTHASH) {
                 CU(shb::launch_nthash_long(fused_upper, res, offs, n, slot_of[a], st));
+            } else if (long_mode && a == SHB_XXH3) {
+                CU(shb::launch_xxh3_long(fused_upper, res, offs, n, slot_of[a], st));
             } else if (long_mode && a == SHB_BLAKE3 && d_scratch) {
                 ScratchLayout L(total_bytes, n);
                 CU(shb::launch_blake3_long(fused_upper, res, offs, n, total_bytes, slot_of[a],
@@ -432,6 +436,7 @@ struct shb_textproc {
     uint32_t *d_out_len = nullptr;
     long long *d_out_off = nullptr;
     uint8_t *d_label = nullptr;
+    void *d_fmt_scan = nullptr;
     uint8_t *d_dig = nullptr;
     size_t dig_cap = 0;
     void *d_scratch = nullptr;
@@ -440,6 +445,8 @@ struct shb_textproc {
     size_t out_cap = 0;
     // results of the last run
     size_t out_bytes = 0, consumed = 0, n_records = 0, n_empty = 0;
+    cudaEvent_t ev[6] = {};     // start, after H2D, after split, after hash, after format, after D2H
+    float ms[5] = {};
 };
 
 shb_textproc *shb_textproc_create(int device, size_t max_text_bytes)
@@ -466,7 +473,9 @@ shb_textproc *shb_textproc_create(int device, size_t max_text_bytes)
               cudaMalloc(&t->rec.name_len, nr * 4) == cudaSuccess && cudaMalloc(&t->rec.qual_start, nr * 8) == cudaSuccess &&
               cudaMalloc(&t->rec.qual_len, nr * 4) == cudaSuccess && cudaMalloc(&t->rec.rec_start, (nr + 1) * 8) == cudaSuccess &&
               cudaMalloc(&t->d_out_len, (nr + 1) * 4) == cudaSuccess && cudaMalloc(&t->d_out_off, (nr + 1) * 8) == cudaSuccess &&
-              cudaMalloc(&t->d_label, 4096) == cudaSuccess;
+              cudaMalloc(&t->d_label, 4096) == cudaSuccess &&
+              cudaMalloc(&t->d_fmt_scan, shb::scan_tmp_bytes(nr + 1)) == cudaSuccess;
+    for (int k = 0; ok && k < 6; k++) ok = cudaEventCreate(&t->ev[k]) == cudaSuccess;
     if (!ok) {
         fail(SHB_ERR_CUDA, std::string("textproc allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
         shb_textproc_destroy(t);
@@ -482,11 +491,12 @@ void shb_textproc_destroy(shb_textproc *t)
     if (!t) return;
     cudaSetDevice(t->device);
     if (t->stream) { cudaStreamSynchronize(t->stream); cudaStreamDestroy(t->stream); }
+    for (int k = 0; k < 6; k++) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
     cudaFreeHost(t->h_text); cudaFreeHost(t->h_info); cudaFreeHost(t->h_out);
     cudaFree(t->d_text); cudaFree(t->d_res); cudaFree(t->d_parse_scratch); cudaFree(t->d_info);
     cudaFree(t->rec.offsets); cudaFree(t->rec.name_start); cudaFree(t->rec.name_len); cudaFree(t->rec.qual_start);
     cudaFree(t->rec.qual_len); cudaFree(t->rec.rec_start); cudaFree(t->d_out_len); cudaFree(t->d_out_off);
-    cudaFree(t->d_label); cudaFree(t->d_dig); cudaFree(t->d_scratch); cudaFree(t->d_out);
+    cudaFree(t->d_label); cudaFree(t->d_fmt_scan); cudaFree(t->d_dig); cudaFree(t->d_scratch); cudaFree(t->d_out);
     delete t;
 }
 
@@ -509,11 +519,15 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
     if (is_final && t->h_text[n_bytes - 1] != '\n') t->h_text[n_bytes++] = '\n';   // the pinned buffer has 64 spare bytes
     std::memset(t->h_text + n_bytes, 0, 32);
     cudaStream_t st = t->stream;
+    for (float &m : t->ms) m = 0.f;
+    CU(cudaEventRecord(t->ev[0], st));
     CU(cudaMemcpyAsync(t->d_text, t->h_text, align_up(n_bytes + 16, 16), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(t->ev[1], st));
     if (label_len) CU(cudaMemcpyAsync(t->d_label, label, label_len, cudaMemcpyHostToDevice, st));
     // 1. split into records (CSR residues + name / quality spans)
     CU(shb::launch_fx_parse(t->d_text, n_bytes, format == SHB_FORMAT_FASTQ, is_final != 0, t->rec, t->d_info, t->d_parse_scratch, st));
     CU(cudaMemcpyAsync(t->h_info, t->d_info, sizeof(shb::FxInfo), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(t->ev[2], st));
     CU(cudaStreamSynchronize(st));
     if (t->h_info->status == shb::FX_BAD_MARKER) return fail(SHB_ERR_FORMAT, "fastx: invalid FASTA/Q format");
     if (t->h_info->status == shb::FX_TOO_MANY_RECORDS) return fail(SHB_ERR_CAPACITY, "more records than the textproc can index; use smaller chunks");
@@ -542,6 +556,7 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
     if (int rc = run_pipeline(t->d_res, reinterpret_cast<const int64_t *>(t->rec.offsets), n, total, algos, n_algos,
                               flags & SHB_FLAG_UPPER, d_slots.data(), nullptr, t->d_scratch, st, nullptr, nullptr))
         return rc;
+    CU(cudaEventRecord(t->ev[3], st));
     // 3. format: `file;h1;..;hn;Name` (+ record body), seqhasher.go:261-282
     shb::FmtCfg cfg{};
     cfg.label = t->d_label;
@@ -552,7 +567,7 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
     cfg.headers_only = headers_only;
     cfg.fastq = format == SHB_FORMAT_FASTQ;
     cfg.upper = (flags & SHB_FLAG_UPPER) ? 1 : 0;
-    CU(shb::launch_fx_format(cfg, t->rec, n, t->d_text, t->d_out_len, t->d_out_off, nullptr, t->d_info, true, st));
+    CU(shb::launch_fx_format(cfg, t->rec, n, t->d_text, t->d_out_len, t->d_out_off, nullptr, t->d_info, true, t->d_fmt_scan, st));
     CU(cudaMemcpyAsync(&t->h_info->reserved, t->d_out_off + n, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&t->h_info->n_empty, &t->d_info->n_empty, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -566,9 +581,12 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
         CU(cudaHostAlloc(&t->h_out, want, cudaHostAllocDefault));
         t->out_cap = want;
     }
-    CU(shb::launch_fx_format(cfg, t->rec, n, t->d_text, t->d_out_len, t->d_out_off, t->d_out, t->d_info, false, st));
+    CU(shb::launch_fx_format(cfg, t->rec, n, t->d_text, t->d_out_len, t->d_out_off, t->d_out, t->d_info, false, t->d_fmt_scan, st));
+    CU(cudaEventRecord(t->ev[4], st));
     CU(cudaMemcpyAsync(t->h_out, t->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(t->ev[5], st));
     CU(cudaStreamSynchronize(st));
+    for (int k = 0; k < 5; k++) cudaEventElapsedTime(&t->ms[k], t->ev[k], t->ev[k + 1]);
     t->out_bytes = out_bytes;
     return SHB_OK;
 }
@@ -580,6 +598,10 @@ const uint8_t *shb_textproc_output(shb_textproc *t, size_t *out_bytes)
     return t->h_out;
 }
 size_t shb_textproc_consumed(shb_textproc *t) { return t ? t->consumed : 0; }
+void shb_textproc_last_ms(shb_textproc *t, float *ms5)
+{
+    for (int k = 0; k < 5; k++) ms5[k] = t ? t->ms[k] : 0.f;
+}
 size_t shb_textproc_records(shb_textproc *t) { return t ? t->n_records : 0; }
 size_t shb_textproc_empty_records(shb_textproc *t) { return t ? t->n_empty : 0; }
 

@@ -145,11 +145,85 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t *__res
     if (hi == nb && lo <= nb) prefix[nb] = run;   // several threads may write the same total
 }
 
-// exclusive scan of n uint32 counts into n+1 int64 prefixes (used by the BLAKE3 long path too)
-cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, cudaStream_t st)
+// ---- general exclusive scan: n uint32 counts -> n+1 int64 prefixes (strip pre-pass, BLAKE3 chunk bases,
+// record splitter, formatter).  Three phases over tiles of 4096 counts: tile sums, scan of the tile sums by
+// one CTA, per-tile scan seeded with its base.  tile_sums needs ceil(n/4096) uint32 + (that + 1) int64.
+constexpr uint32_t SCAN_TILE = 4096;   // 256 threads x 16 counts
+
+__global__ void __launch_bounds__(256) scan_tile_sum_kernel(const uint32_t *__restrict__ counts, size_t n,
+                                                            uint32_t *__restrict__ tile_sums)
 {
-    scan_blocks_kernel<<<1, 1024, 0, st>>>(counts, n, prefix);
-    g_launches++;
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + 16u * threadIdx.x;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+        if (base + k < n) s += counts[base + k];
+    __shared__ uint32_t s_w[8];
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += s_w[i];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) scan_tile_apply_kernel(const uint32_t *__restrict__ counts, size_t n,
+                                                              const int64_t *__restrict__ tile_base,
+                                                              int64_t *__restrict__ prefix)
+{
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + 16u * threadIdx.x;
+    uint32_t v[16];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { v[k] = (base + k < n) ? counts[base + k] : 0u; s += v[k]; }
+    __shared__ uint32_t s_w[8];
+    uint32_t incl = s;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((threadIdx.x & 31) >= d) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int64_t run = tile_base[blockIdx.x] + (incl - s);
+    for (uint32_t i = 0; i < (threadIdx.x >> 5); i++) run += s_w[i];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (base + k < n) prefix[base + k] = run;
+        run += v[k];
+    }
+    // the closing element prefix[n] = grand total is written by scan_blocks_kernel's tile_base[ntiles]
+}
+
+__global__ void scan_close_kernel(const int64_t *__restrict__ tile_base, size_t ntiles, size_t n, int64_t *__restrict__ prefix)
+{
+    prefix[n] = tile_base[ntiles];
+}
+
+size_t scan_tmp_bytes(size_t n)
+{
+    const size_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    return ((ntiles + 64) * 4 + 7) / 8 * 8 + (ntiles + 64) * 8;
+}
+
+// tmp: scan_tmp_bytes(n) bytes owned by the caller (so scans on different streams never share it)
+cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, void *tmp, cudaStream_t st)
+{
+    if (n <= 65536 || tmp == nullptr) {   // small inputs: one CTA does it all
+        scan_blocks_kernel<<<1, 1024, 0, st>>>(counts, n, prefix);
+        g_launches++;
+        return cudaGetLastError();
+    }
+    const size_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t *tile_sums = static_cast<uint32_t *>(tmp);
+    int64_t *tile_base = reinterpret_cast<int64_t *>(static_cast<uint8_t *>(tmp) + ((ntiles + 64) * 4 + 7) / 8 * 8);
+    scan_tile_sum_kernel<<<(unsigned)ntiles, 256, 0, st>>>(counts, n, tile_sums);
+    scan_blocks_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles, tile_base);
+    scan_tile_apply_kernel<<<(unsigned)ntiles, 256, 0, st>>>(counts, n, tile_base, prefix);
+    scan_close_kernel<<<1, 1, 0, st>>>(tile_base, ntiles, n, prefix);
+    g_launches += 4;
     return cudaGetLastError();
 }
 
@@ -228,12 +302,15 @@ cudaError_t launch_lengths(const int64_t *offs, size_t n, int64_t *out_len, cuda
 
 cudaError_t launch_normalise(const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes, bool strip,
                              bool upper, uint32_t *block_counts, int64_t *block_prefix, uint8_t *out_res,
-                             int64_t *out_offs, int64_t *out_len, cudaStream_t st)
+                             int64_t *out_offs, int64_t *out_len, void *scan_tmp, cudaStream_t st)
 {
     const size_t nb = norm_blocks(total_bytes);
     if (strip) nz_count_kernel<true><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, block_counts);
     else nz_count_kernel<false><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, block_counts);
-    scan_blocks_kernel<<<1, 1024, 0, st>>>(block_counts, nb, block_prefix);
+    {
+        cudaError_t es = scan_counts(block_counts, nb, block_prefix, scan_tmp, st);
+        if (es != cudaSuccess) return es;
+    }
     if (strip && upper)
         compact_kernel<true, true><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs);
     else if (strip)
@@ -242,7 +319,7 @@ cudaError_t launch_normalise(const uint8_t *res, const int64_t *offs, size_t n, 
         compact_kernel<false, true><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs);
     else
         compact_kernel<false, false><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs);
-    g_launches += 3;
+    g_launches += 2;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (out_len) return launch_lengths(out_offs, n, out_len, st);

@@ -42,6 +42,7 @@ uint32_t tile_fast_mask();
 // list + thread-per-record tree merge (scratch: b3_long_scratch_bytes()).
 cudaError_t launch_nthash_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, uint8_t *out,
                                cudaStream_t st);
+cudaError_t launch_xxh3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, uint8_t *out, cudaStream_t st);
 size_t b3_long_scratch_bytes(size_t total_bytes, size_t n);
 cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
                                uint8_t *out, void *scratch, cudaStream_t st);
@@ -51,7 +52,12 @@ cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *of
 // block_counts: norm_blocks() uint32; block_prefix: norm_blocks()+1 int64.
 cudaError_t launch_normalise(const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes, bool strip,
                              bool upper, uint32_t *block_counts, int64_t *block_prefix, uint8_t *out_res,
-                             int64_t *out_offs, int64_t *out_len, cudaStream_t st);
+                             int64_t *out_offs, int64_t *out_len, void *scan_tmp, cudaStream_t st);
+
+// Exclusive scan of n uint32 counts into n+1 int64 prefixes; tmp = scan_tmp_bytes(n) caller-owned bytes
+// (nullptr: single-CTA scan, fine for small n).
+size_t scan_tmp_bytes(size_t n);
+cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, void *tmp, cudaStream_t st);
 
 cudaError_t launch_lengths(const int64_t *offs, size_t n, int64_t *out_len, cudaStream_t st);
 

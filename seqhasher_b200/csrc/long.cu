@@ -108,6 +108,137 @@ cudaError_t launch_nthash_long(bool upper, const uint8_t *res, const int64_t *of
     return cudaGetLastError();
 }
 
+// --------------------------------------------------------------------------------------------- XXH3
+
+// 16 bytes at any address as 4 LE words: two aligned 128-bit loads + funnel shift (m is warp-uniform here)
+template <bool UPPER>
+__device__ __forceinline__ void load16_any(const uint8_t *p, uint32_t (&w)[4])
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>((uintptr_t)p & ~(uintptr_t)15);
+    const uint32_t m = (uint32_t)((uintptr_t)p & 15u);
+    const uint4 a = __ldg(q);
+    uint4 b = make_uint4(0, 0, 0, 0);
+    if (m) b = __ldg(q + 1);
+    const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t sh = (m & 3u) * 8u;
+    switch (m >> 2) {
+    case 0:
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = __funnelshift_r(u[i], u[i + 1], sh);
+        break;
+    case 1:
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = __funnelshift_r(u[i + 1], u[i + 2], sh);
+        break;
+    case 2:
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = __funnelshift_r(u[i + 2], u[i + 3], sh);
+        break;
+    default:
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = __funnelshift_r(u[i + 3], u[i + 4], sh);
+        break;
+    }
+    if (UPPER) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = upper4(w[i]);
+    }
+}
+
+// 64-bit LE word of the secret copy in shared memory at any byte offset
+__device__ __forceinline__ uint64_t ssec(const uint32_t *sec, uint32_t off)
+{
+    const uint32_t i = off >> 2, s = (off & 3u) * 8u;
+    const uint32_t w0 = sec[i], w1 = sec[i + 1], w2 = sec[i + 2];
+    return mk64(__funnelshift_r(w0, w1, s), __funnelshift_r(w1, w2, s));
+}
+
+// Warp per record, records > 240 bytes (the XXH3 "long" path, A.12): lane = 4*sub + pair owns accumulators
+// (2*pair, 2*pair+1) of stripes sub and sub+8 of every 1024-byte block; one warp load covers 8 consecutive
+// stripes (512 contiguous bytes).  Stripes inside a block commute, so the 8 sub-groups are summed with
+// shuffles before the per-block scramble.  Shorter records fall to lane 0 running the generic routine.
+template <bool UPPER>
+__global__ void __launch_bounds__(256) xxh3_warp_kernel(const uint8_t *__restrict__ res, const int64_t *__restrict__ offs,
+                                                        size_t n, uint8_t *__restrict__ out)
+{
+    __shared__ uint32_t sec[52];
+    if (threadIdx.x < 50) sec[threadIdx.x] = reinterpret_cast<const uint32_t *>(c_xxh3_secret)[threadIdx.x];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, sub = lane >> 2, pair = lane & 3u;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    constexpr uint64_t INIT[8] = {XP32_3, XP64_1, XP64_2, XP64_3, XP64_4, XP32_2, XP64_5, XP32_1};
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const int64_t s = offs[i];
+        const uint64_t len = (uint64_t)(offs[i + 1] - s);
+        uint8_t *o = out + i * 8;
+        if (len <= 240) {
+            if (lane == 0) {
+                if (len == 0) *reinterpret_cast<uint2 *>(o) = make_uint2(0u, 0u);
+                else { GlobalReader<UPPER> r(res, s); store_be64(o, xxh3_record(r, (uint32_t)len)); }
+            }
+            continue;
+        }
+        const uint8_t *p = res + s;
+        const uint64_t init0 = pair == 0 ? INIT[0] : pair == 1 ? INIT[2] : pair == 2 ? INIT[4] : INIT[6];
+        const uint64_t init1 = pair == 0 ? INIT[1] : pair == 1 ? INIT[3] : pair == 2 ? INIT[5] : INIT[7];
+        uint64_t a0 = sub == 0 ? init0 : 0, a1 = sub == 0 ? init1 : 0;   // sub 0 carries the state, the others deltas
+        const uint64_t nblocks = (len - 1) >> 10;
+        const uint32_t tail_stripes = (uint32_t)(((len - 1) - (nblocks << 10)) >> 6);
+        for (uint64_t b = 0; b <= nblocks; b++) {
+            const bool last = b == nblocks;
+            const uint32_t nst = last ? tail_stripes : 16u;
+#pragma unroll
+            for (uint32_t half = 0; half < 2; half++) {
+                const uint32_t st = sub + 8u * half;
+                if (st < nst) {
+                    uint32_t w[4];
+                    load16_any<UPPER>(p + (b << 10) + 64u * st + 16u * pair, w);
+                    const uint64_t d0 = mk64(w[0], w[1]), d1 = mk64(w[2], w[3]);
+                    const uint64_t k0 = d0 ^ ssec(sec, 8u * st + 16u * pair), k1 = d1 ^ ssec(sec, 8u * st + 16u * pair + 8u);
+                    a0 += d1 + (uint64_t)(uint32_t)k0 * (uint64_t)(uint32_t)(k0 >> 32);
+                    a1 += d0 + (uint64_t)(uint32_t)k1 * (uint64_t)(uint32_t)(k1 >> 32);
+                }
+            }
+            // sum the 8 sub-groups (lane bits 2..4)
+#pragma unroll
+            for (int d = 4; d < 32; d <<= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, d);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+            }
+            if (!last) {   // scramble (every lane holds the block sum), then only sub 0 keeps it
+                a0 = (a0 ^ (a0 >> 47) ^ ssec(sec, 128u + 16u * pair)) * XP32_1;
+                a1 = (a1 ^ (a1 >> 47) ^ ssec(sec, 136u + 16u * pair)) * XP32_1;
+                if (sub) { a0 = 0; a1 = 0; }
+            }
+        }
+        // last stripe at len-64 with the secret at 121, then the merge; lanes 0..3 (sub 0) each own one pair
+        uint64_t term = 0;
+        if (sub == 0) {
+            uint32_t w[4];
+            load16_any<UPPER>(p + len - 64 + 16u * pair, w);
+            const uint64_t d0 = mk64(w[0], w[1]), d1 = mk64(w[2], w[3]);
+            const uint64_t k0 = d0 ^ ssec(sec, 121u + 16u * pair), k1 = d1 ^ ssec(sec, 129u + 16u * pair);
+            a0 += d1 + (uint64_t)(uint32_t)k0 * (uint64_t)(uint32_t)(k0 >> 32);
+            a1 += d0 + (uint64_t)(uint32_t)k1 * (uint64_t)(uint32_t)(k1 >> 32);
+            term = mulfold64(a0 ^ ssec(sec, 11u + 16u * pair), a1 ^ ssec(sec, 19u + 16u * pair));
+        }
+        term += __shfl_xor_sync(0xffffffffu, term, 1);
+        term += __shfl_xor_sync(0xffffffffu, term, 2);
+        if (lane == 0) store_be64(o, xxh3_avalanche(len * XP64_1 + term));
+    }
+}
+
+cudaError_t launch_xxh3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, uint8_t *out, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n + 7) / 8;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    if (upper) xxh3_warp_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(res, offs, n, out);
+    else xxh3_warp_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(res, offs, n, out);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------- BLAKE3
 
 // chunks of record i = max(1, ceil(len/1024)); written as uint32 counts for the shared scan kernel
@@ -269,10 +400,9 @@ size_t b3_long_scratch_bytes(size_t total_bytes, size_t n)
 {
     const size_t max_chunks = total_bytes / 1024 + n + 1;
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    return up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)) + up(max_chunks * 32);
+    return up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)) + up(max_chunks * 32) + up(scan_tmp_bytes(n));
 }
 
-cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, cudaStream_t st);   // kernels.cu
 
 cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
                                uint8_t *out, void *scratch, cudaStream_t st)
@@ -285,7 +415,9 @@ cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *of
     uint32_t *cvs = reinterpret_cast<uint32_t *>(base + up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)));
     b3_count_chunks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(offs, n, counts);
     g_launches++;
-    cudaError_t e = scan_counts(counts, n, chunk_base, st);
+    const size_t max_chunks0 = total_bytes / 1024 + n + 1;
+    void *scan_tmp = base + up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)) + up(max_chunks0 * 32);
+    cudaError_t e = scan_counts(counts, n, chunk_base, scan_tmp, st);
     if (e != cudaSuccess) return e;
     const size_t max_chunks = total_bytes / 1024 + n + 1;   // upper bound of chunk_base[n]; the kernel re-checks
     const unsigned blocks = (unsigned)((max_chunks + 127) / 128);

@@ -26,6 +26,39 @@ constexpr int FX_THREADS = 256;   // 16 bytes per thread, FX_BLK = 4096
 
 __device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[4], int j) { return (w[j >> 2] >> (8 * (j & 3))) & 0xffu; }
 
+// bit k of the result = byte k of w equals c (exact; SWAR zero-byte test on w ^ c)
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t c4)
+{
+    const uint32_t z = w ^ c4;
+    const uint32_t m = ~(((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z | 0x7f7f7f7fu);   // 0x80 where the byte is zero
+    return ((m >> 7) * 0x00204081u) >> 21 & 0xfu;                                  // gather bits 0,8,16,24 -> 0..3
+}
+// 16-bit masks over the thread's 16 bytes: newlines, whitespace (\t \n \v \f \r ' '), bytes inside the text
+__device__ __forceinline__ uint32_t nl_mask16(const uint32_t (&w)[4])
+{
+    return eq_mask4(w[0], 0x0a0a0a0au) | eq_mask4(w[1], 0x0a0a0a0au) << 4 | eq_mask4(w[2], 0x0a0a0a0au) << 8 |
+           eq_mask4(w[3], 0x0a0a0a0au) << 12;
+}
+__device__ __forceinline__ uint32_t ws_mask16(const uint32_t (&w)[4])
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        // c == 0x20 or 9 <= c <= 13: bytes below 0x0e with bit pattern >= 9, tested per byte without carries
+        const uint32_t x = w[k];
+        const uint32_t lo7 = x & 0x7f7f7f7fu;
+        const uint32_t ge9 = lo7 + 0x77777777u;     // bit7 set <=> (c & 0x7f) >= 9
+        const uint32_t ge14 = lo7 + 0x72727272u;    // bit7 set <=> (c & 0x7f) >= 14
+        const uint32_t ctl = ge9 & ~ge14 & ~x & 0x80808080u;
+        m |= ((((ctl >> 7) * 0x00204081u) >> 21 & 0xfu) | eq_mask4(x, 0x20202020u)) << (4 * k);
+    }
+    return m;
+}
+__device__ __forceinline__ uint32_t valid_mask16(size_t pos, size_t n)
+{
+    return pos + 16 <= n ? 0xffffu : (pos < n ? (1u << (uint32_t)(n - pos)) - 1u : 0u);
+}
+
 __global__ void __launch_bounds__(FX_THREADS) fx_lines_kernel(const uint8_t *__restrict__ text, size_t n,
                                                               long long *__restrict__ blk_last_nl,
                                                               uint32_t *__restrict__ blk_nl_count)
@@ -36,9 +69,9 @@ __global__ void __launch_bounds__(FX_THREADS) fx_lines_kernel(const uint8_t *__r
     if (pos < n) {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + pos));
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 16; j++)
-            if (pos + j < n && byte_of(w, j) == '\n') { last = (long long)(pos + j); cnt++; }
+        const uint32_t m = nl_mask16(w) & valid_mask16(pos, n);
+        cnt = __popc(m);
+        if (m) last = (long long)pos + (31 - __clz(m));
     }
     __shared__ long long s_last[FX_THREADS / 32];
     __shared__ uint32_t s_cnt[FX_THREADS / 32];
@@ -90,6 +123,59 @@ __global__ void __launch_bounds__(1024) fx_scan_kernel(const long long *__restri
     if (threadIdx.x == 1023) { prev_nl[nb] = s_mx[1023]; nl_before[nb] = s_sum[1023]; }
 }
 
+// Large inputs: the same scan in three phases over tiles of 1024 blocks (one block summary per thread).
+__global__ void __launch_bounds__(1024) fx_tile_reduce_kernel(const long long *__restrict__ blk_last_nl,
+                                                              const uint32_t *__restrict__ blk_nl_count, size_t nb,
+                                                              long long *__restrict__ tile_last, uint32_t *__restrict__ tile_cnt)
+{
+    const size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    long long mx = i < nb ? blk_last_nl[i] : -1;
+    uint32_t cnt = i < nb ? blk_nl_count[i] : 0;
+    __shared__ long long s_mx[32];
+    __shared__ uint32_t s_cnt[32];
+    for (int d = 16; d; d >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    }
+    if ((threadIdx.x & 31) == 0) { s_mx[threadIdx.x >> 5] = mx; s_cnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; k++) { mx = max(mx, s_mx[k]); cnt += s_cnt[k]; }
+        tile_last[blockIdx.x] = mx;
+        tile_cnt[blockIdx.x] = cnt;
+    }
+}
+
+__global__ void __launch_bounds__(1024) fx_tile_apply_kernel(const long long *__restrict__ blk_last_nl,
+                                                             const uint32_t *__restrict__ blk_nl_count, size_t nb,
+                                                             const long long *__restrict__ tile_prev, const long long *__restrict__ tile_before,
+                                                             size_t ntiles, long long *__restrict__ prev_nl, long long *__restrict__ nl_before)
+{
+    __shared__ long long s_mx[1024], s_sum[1024];
+    const size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    const long long my_mx = i < nb ? blk_last_nl[i] : -1;
+    const long long my_cnt = i < nb ? (long long)blk_nl_count[i] : 0;
+    s_mx[threadIdx.x] = my_mx;
+    s_sum[threadIdx.x] = my_cnt;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        long long a = -1, b = 0;
+        if ((int)threadIdx.x >= d) { a = s_mx[threadIdx.x - d]; b = s_sum[threadIdx.x - d]; }
+        __syncthreads();
+        if ((int)threadIdx.x >= d) { s_mx[threadIdx.x] = max(s_mx[threadIdx.x], a); s_sum[threadIdx.x] += b; }
+        __syncthreads();
+    }
+    const long long base_mx = tile_prev[blockIdx.x], base_sum = tile_before[blockIdx.x];
+    if (i < nb) {
+        prev_nl[i] = max(base_mx, threadIdx.x ? s_mx[threadIdx.x - 1] : -1);
+        nl_before[i] = base_sum + (threadIdx.x ? s_sum[threadIdx.x - 1] : 0);
+    }
+    if (blockIdx.x == ntiles - 1 && threadIdx.x == 0) {   // totals
+        prev_nl[nb] = tile_prev[ntiles];
+        nl_before[nb] = tile_before[ntiles];
+    }
+}
+
 // Classify the block's bytes.  Thread t owns bytes [bstart + 16t, +16).  The line state entering the
 // thread's chunk (start of the current line, its index) comes from a block-wide exclusive scan of
 // (last newline position, newline count) seeded with the per-block prefixes.  A record "event" is the
@@ -113,10 +199,8 @@ __global__ void __launch_bounds__(FX_THREADS) fx_emit_kernel(const uint8_t *__re
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     }
     // --- phase A: newline summary of my chunk, block-exclusive scan (max position, count) ---
-    uint32_t nl_mask = 0;
-#pragma unroll
-    for (int j = 0; j < 16; j++)
-        if (pos + j < n && byte_of(w, j) == '\n') nl_mask |= 1u << j;
+    const uint32_t valid = valid_mask16(pos, n);
+    const uint32_t nl_mask = nl_mask16(w) & valid;
     const long long my_last = nl_mask ? (long long)pos + (31 - __clz(nl_mask)) : -1;
     const uint32_t my_cnt = __popc(nl_mask);
     long long inc_last = my_last;
@@ -137,23 +221,26 @@ __global__ void __launch_bounds__(FX_THREADS) fx_emit_kernel(const uint8_t *__re
         if (lane) { prev_nl = max(prev_nl, a); nl_before += b; }
     }
     __syncthreads();   // s_b is reused below
-    // --- phase B: walk my 16 bytes with the line state ---
+    // --- phase B: my 16 bytes are cut into segments by their newlines; a segment shares one line state ---
     long long line_start = prev_nl + 1;
     long long line_no = nl_before;
     bool header_line = !FASTQ && pos < n && text[line_start] == '>';   // FASTA: line starts with '>'
+    const uint32_t cand = ~ws_mask16(w) & valid;   // non-blank bytes inside the text
     uint32_t kept_mask = 0, ev_mask = 0;
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const uint32_t c = byte_of(w, j);
-        if ((nl_mask >> j) & 1u) {
+    {
+        uint32_t m = nl_mask, seg_lo = 0;
+        while (true) {
+            const uint32_t j = m ? (uint32_t)__ffs(m) - 1u : 16u;        // next newline (16 = end of chunk)
+            const bool seq_line = FASTQ ? ((line_no & 3) == 1) : !header_line;
+            if (seq_line) kept_mask |= cand & ((1u << j) - 1u) & ~((1u << seg_lo) - 1u);
+            if (j == 16u) break;
             const bool name_line = FASTQ ? ((line_no & 3) == 0) : header_line;
             if (name_line) ev_mask |= 1u << j;
             line_start = (long long)(pos + j) + 1;
             line_no++;
             if (!FASTQ) header_line = (size_t)line_start < n && text[line_start] == '>';
-        } else if (pos + j < n) {
-            const bool seq_line = FASTQ ? ((line_no & 3) == 1) : !header_line;
-            if (seq_line && !is_ws(c)) kept_mask |= 1u << j;
+            seg_lo = j + 1;
+            m &= m - 1;
         }
     }
     const uint32_t my_kept = __popc(kept_mask), my_ev = __popc(ev_mask);
@@ -173,42 +260,77 @@ __global__ void __launch_bounds__(FX_THREADS) fx_emit_kernel(const uint8_t *__re
         }
         return;
     }
-    long long kept_run = kept_before_blk[blockIdx.x] + inc_k - my_kept;
+    const long long blk_base = kept_before_blk[blockIdx.x];
+    uint32_t local_excl = inc_k - my_kept;
     long long rec_run = recs_before_blk[blockIdx.x] + inc_e - my_ev;
-    for (uint32_t k = 0; k < wid; k++) { kept_run += s_b[k]; rec_run += s_c[k]; }
+    uint32_t blk_total = 0;
+    for (uint32_t k = 0; k < FX_THREADS / 32; k++) {
+        if (k < wid) { local_excl += s_b[k]; rec_run += s_c[k]; }
+        blk_total += s_b[k];
+    }
+    long long kept_run = blk_base + local_excl;
+    // The block's residues form one contiguous run of the output.  They are compacted in shared memory at
+    // the same 16-byte phase as their destination, then copied out with aligned 128-bit stores.
+    __shared__ __align__(16) uint8_t s_out[FX_BLK + 32];
+    const uint32_t phase = (uint32_t)(blk_base & 15);
     // --- scatter ---
     line_start = prev_nl + 1;
     line_no = nl_before;
-    uint8_t *dst = out.residues + kept_run;
+    {
+        uint8_t *dst = s_out + phase + local_excl;
+        if (kept_mask == 0xffffu) {
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const long long p = (long long)(pos + j);
-        if ((kept_mask >> j) & 1u) { *dst++ = (uint8_t)byte_of(w, j); kept_run++; }
-        if ((nl_mask >> j) & 1u) {
-            long long le = p;                                   // line end, '\r' of a CRLF break dropped
-            if (le > line_start && text[le - 1] == '\r') le--;
-            if ((ev_mask >> j) & 1u) {
-                const long long r = rec_run++;
-                if (r < out.max_records) {
-                    out.name_start[r] = line_start + 1;         // skip '>' / '@'
-                    out.name_len[r] = (int)(le - line_start - 1 > 0 ? le - line_start - 1 : 0);
-                    out.offsets[r] = kept_run;                  // nothing of a name line is ever kept
-                    out.rec_start[r] = line_start;
-                    if (text[line_start] != (FASTQ ? '@' : '>')) info->status = FX_BAD_MARKER;
-                } else {
-                    info->status = FX_TOO_MANY_RECORDS;
-                }
-            } else if (FASTQ) {
-                const long long kind = line_no & 3;
-                const long long r = rec_run - 1;                // the record this line belongs to
-                if (kind == 2 && text[line_start] != '+') info->status = FX_BAD_MARKER;
-                if (kind == 3 && r >= 0 && r < out.max_records) {
-                    out.qual_start[r] = line_start;
-                    out.qual_len[r] = (int)(le - line_start);
-                }
+            for (int j = 0; j < 16; j++) dst[j] = (uint8_t)byte_of(w, j);
+        } else {
+            uint32_t km = kept_mask;
+            while (km) {
+                const int j = __ffs(km) - 1;
+                *dst++ = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+                km &= km - 1;
             }
-            line_start = p + 1;
-            line_no++;
+        }
+    }
+    for (uint32_t m = nl_mask; m; m &= m - 1) {
+        const uint32_t j = (uint32_t)__ffs(m) - 1u;
+        const long long p = (long long)(pos + j);
+        const long long kept_here = kept_run + __popc(kept_mask & ((1u << j) - 1u));   // residues before this newline
+        long long le = p;                                   // line end, '\r' of a CRLF break dropped
+        if (le > line_start && text[le - 1] == '\r') le--;
+        if ((ev_mask >> j) & 1u) {
+            const long long r = rec_run++;
+            if (r < out.max_records) {
+                out.name_start[r] = line_start + 1;         // skip '>' / '@'
+                out.name_len[r] = (int)(le - line_start - 1 > 0 ? le - line_start - 1 : 0);
+                out.offsets[r] = kept_here;                 // nothing of a name line is ever kept
+                out.rec_start[r] = line_start;
+                if (text[line_start] != (FASTQ ? '@' : '>')) info->status = FX_BAD_MARKER;
+            } else {
+                info->status = FX_TOO_MANY_RECORDS;
+            }
+        } else if (FASTQ) {
+            const long long kind = line_no & 3;
+            const long long r = rec_run - 1;                // the record this line belongs to
+            if (kind == 2 && text[line_start] != '+') info->status = FX_BAD_MARKER;
+            if (kind == 3 && r >= 0 && r < out.max_records) {
+                out.qual_start[r] = line_start;
+                out.qual_len[r] = (int)(le - line_start);
+            }
+        }
+        line_start = p + 1;
+        line_no++;
+    }
+    __syncthreads();
+    // copy-out: 16-byte unit u of s_out <-> global (blk_base & ~15) + 16u; edge units byte by byte
+    {
+        uint8_t *gbase = out.residues + (blk_base - phase);
+        const uint32_t end = phase + blk_total;                 // valid bytes are s_out[phase, end)
+        for (uint32_t u = threadIdx.x; u * 16u < end; u += FX_THREADS) {
+            const uint32_t lo = u * 16u, hi = lo + 16u;
+            if (lo >= phase && hi <= end) {
+                *reinterpret_cast<uint4 *>(gbase + lo) = *reinterpret_cast<const uint4 *>(s_out + lo);
+            } else {
+                for (uint32_t k = (lo > phase ? lo : phase); k < (hi < end ? hi : end); k++) gbase[k] = s_out[k];
+            }
         }
     }
 }
@@ -339,14 +461,15 @@ __global__ void __launch_bounds__(256) fmt_write_kernel(FmtCfg c, FxOut rec, siz
 
 // ------------------------------------------------------------------------------------------- launchers
 
-cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, cudaStream_t st);   // kernels.cu
 
 size_t fx_scratch_bytes(size_t n_bytes)
 {
     const size_t nb = n_bytes / FX_BLK + 1;
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     // last_nl, nl_count, prev_nl, nl_before, blk_kept, blk_recs, kept_prefix, rec_prefix
-    return up(nb * 8) + up(nb * 4) + 2 * up((nb + 1) * 8) + 2 * up(nb * 4) + 2 * up((nb + 1) * 8);
+    const size_t nt = nb / 1024 + 2;
+    return up(nb * 8) + up(nb * 4) + 2 * up((nb + 1) * 8) + 2 * up(nb * 4) + 2 * up((nb + 1) * 8) + up(scan_tmp_bytes(nb)) +
+           up(nt * 8) + up(nt * 4) + 2 * up((nt + 1) * 8);
 }
 
 cudaError_t launch_fx_parse(const uint8_t *text, size_t n, bool fastq, bool is_final, FxOut out, FxInfo *info,
@@ -362,17 +485,31 @@ cudaError_t launch_fx_parse(const uint8_t *text, size_t n, bool fastq, bool is_f
     uint32_t *blk_kept = reinterpret_cast<uint32_t *>(p); p += up(nb * 4);
     uint32_t *blk_recs = reinterpret_cast<uint32_t *>(p); p += up(nb * 4);
     long long *kept_prefix = reinterpret_cast<long long *>(p); p += up((nb + 1) * 8);
-    long long *rec_prefix = reinterpret_cast<long long *>(p);
+    long long *rec_prefix = reinterpret_cast<long long *>(p); p += up((nb + 1) * 8);
+    void *scan_tmp = p; p += up(scan_tmp_bytes(nb));
+    const size_t nt = nb / 1024 + 2;
+    long long *tile_last = reinterpret_cast<long long *>(p); p += up(nt * 8);
+    uint32_t *tile_cnt = reinterpret_cast<uint32_t *>(p); p += up(nt * 4);
+    long long *tile_prev = reinterpret_cast<long long *>(p); p += up((nt + 1) * 8);
+    long long *tile_before = reinterpret_cast<long long *>(p);
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(FxInfo), st);
     if (e != cudaSuccess) return e;
     if (fastq && (e = cudaMemsetAsync(out.qual_len, 0, (size_t)out.max_records * sizeof(int), st)) != cudaSuccess) return e;
     fx_lines_kernel<<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, last_nl, nl_count);
-    fx_scan_kernel<<<1, 1024, 0, st>>>(last_nl, nl_count, nb, prev_nl, nl_before);
+    if (nb <= 4096) {
+        fx_scan_kernel<<<1, 1024, 0, st>>>(last_nl, nl_count, nb, prev_nl, nl_before);
+    } else {
+        const size_t ntiles = (nb + 1023) / 1024;
+        fx_tile_reduce_kernel<<<(unsigned)ntiles, 1024, 0, st>>>(last_nl, nl_count, nb, tile_last, tile_cnt);
+        fx_scan_kernel<<<1, 1024, 0, st>>>(tile_last, tile_cnt, ntiles, tile_prev, tile_before);
+        fx_tile_apply_kernel<<<(unsigned)ntiles, 1024, 0, st>>>(last_nl, nl_count, nb, tile_prev, tile_before, ntiles, prev_nl, nl_before);
+        g_launches += 2;
+    }
     if (fastq) fx_emit_kernel<true, true><<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, prev_nl, nl_before, blk_kept, blk_recs, nullptr, nullptr, out, info);
     else fx_emit_kernel<false, true><<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, prev_nl, nl_before, blk_kept, blk_recs, nullptr, nullptr, out, info);
     g_launches += 3;
-    if ((e = scan_counts(blk_kept, nb, reinterpret_cast<int64_t *>(kept_prefix), st)) != cudaSuccess) return e;
-    if ((e = scan_counts(blk_recs, nb, reinterpret_cast<int64_t *>(rec_prefix), st)) != cudaSuccess) return e;
+    if ((e = scan_counts(blk_kept, nb, reinterpret_cast<int64_t *>(kept_prefix), scan_tmp, st)) != cudaSuccess) return e;
+    if ((e = scan_counts(blk_recs, nb, reinterpret_cast<int64_t *>(rec_prefix), scan_tmp, st)) != cudaSuccess) return e;
     if (fastq) fx_emit_kernel<true, false><<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, prev_nl, nl_before, nullptr, nullptr, kept_prefix, rec_prefix, out, info);
     else fx_emit_kernel<false, false><<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, prev_nl, nl_before, nullptr, nullptr, kept_prefix, rec_prefix, out, info);
     fx_finish_kernel<<<1, 1, 0, st>>>(kept_prefix, rec_prefix, nl_before, prev_nl, nb, n, fastq ? 1 : 0, is_final ? 1 : 0, out, info);
@@ -381,13 +518,14 @@ cudaError_t launch_fx_parse(const uint8_t *text, size_t n, bool fastq, bool is_f
 }
 
 cudaError_t launch_fx_format(const FmtCfg &cfg, const FxOut &rec, size_t n, const uint8_t *text, uint32_t *out_len,
-                             long long *out_off, uint8_t *out, FxInfo *info, bool lengths_only, cudaStream_t st)
+                             long long *out_off, uint8_t *out, FxInfo *info, bool lengths_only, void *scan_tmp,
+                             cudaStream_t st)
 {
     if (lengths_only) {
         if (n) fmt_len_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cfg, rec, n, out_len,
                                                                          reinterpret_cast<unsigned long long *>(&info->n_empty));
         g_launches++;
-        return scan_counts(out_len, n, reinterpret_cast<int64_t *>(out_off), st);
+        return scan_counts(out_len, n, reinterpret_cast<int64_t *>(out_off), scan_tmp, st);
     }
     if (n == 0) return cudaSuccess;
     size_t blocks = (n + 7) / 8;

@@ -45,6 +45,7 @@ cudaError_t launch_fx_parse(const uint8_t *text, size_t n, bool fastq, bool is_f
                             void *scratch, cudaStream_t st);
 // lengths_only: per-record output lengths into out_len + exclusive scan into out_off (n+1); else write the text
 cudaError_t launch_fx_format(const FmtCfg &cfg, const FxOut &rec, size_t n, const uint8_t *text, uint32_t *out_len,
-                             long long *out_off, uint8_t *out, FxInfo *info, bool lengths_only, cudaStream_t st);
+                             long long *out_off, uint8_t *out, FxInfo *info, bool lengths_only, void *scan_tmp,
+                             cudaStream_t st);
 
 }  // namespace shb

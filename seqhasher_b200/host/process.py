@@ -135,7 +135,7 @@ def process_sequences_gpu(input_stream, output_stream, cfg, textproc=None, chunk
                 raise
             for _ in range(nempty * len(ids)):
                 print(EMPTY_MSG, file=log)
-            output_stream.write(out)
+            output_stream.write(memoryview(out))
             if eof:
                 return
             if consumed == 0:

@@ -103,3 +103,18 @@ def test_batch_matches_one_shot_and_threads_agree(oracle):
             want = oracle.get_hash_func(a)(rec)
             got = d1[k][i].tobytes().hex() if n else ""
             assert got == want, (a, i)
+
+
+def test_unpinned_paths_three_way_agreement(oracle):
+    # cityhash >= 16 B and rapidhash > 16 B have no reference vector: an independent pure-Python restatement
+    # (tests/pyref.py) must agree with the C oracle on every length class (the CUDA code is the third, on GPU)
+    import pyref
+    rnd = random.Random(11)
+    assert pyref.cityhash128_hex(b"ACTG") == G.ACTG["cityhash"] and pyref.rapidhash_hex(b"ACTG") == G.ACTG["rapidhash"]
+    assert pyref.cityhash128_hex(b"abc") == G.CITY128_ABC
+    assert int(pyref.rapidhash_hex(b"hello world", final_secret=1), 16) == G.RAPIDHASH_V1_HELLO_WORLD
+    for n in list(range(0, 200)) + [239, 240, 241, 255, 256, 257, 383, 384, 385, 1000, 4097]:
+        d = rnd.randbytes(n)
+        if n:
+            assert oracle.get_hash_func("cityhash")(d) == pyref.cityhash128_hex(d), n
+            assert oracle.get_hash_func("rapidhash")(d) == pyref.rapidhash_hex(d), n

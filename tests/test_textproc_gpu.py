@@ -165,3 +165,16 @@ def test_empty_sequence_log_lines(H):
     tp.close()
     assert out.getvalue().startswith(b">f;;;a\n\n>f;") and out.getvalue().endswith(b">f;;;c\n\n")
     assert log.getvalue().count("Empty DNA sequence") == 4            # 2 empty records x 2 hash types
+
+
+def test_large_text_uses_tiled_scans(H, oracle):
+    # > 4096 scan blocks (16 MiB of text): exercises the tiled (max, sum) block scan and the tiled count scans
+    data = synth_fasta(14000, 21)
+    assert len(data) > 17 << 20
+    cfg = H.Config(hash_types=["xxh3"], headers_only=True, input_file_name="big")
+    got = run_gpu(H, data, cfg, chunk=32 << 20)
+    assert got == expected(oracle, data, cfg)
+    fq = synth_fastq(90000, 22)
+    assert len(fq) > 17 << 20
+    got = run_gpu(H, fq, cfg, chunk=32 << 20)
+    assert got == expected(oracle, fq, cfg)

@@ -55,7 +55,7 @@ def main():
     print(json.dumps({"what": "shb_textproc end to end (host text -> host output)", "records": n, "read_len": a.len,
                       "format": "fastq" if a.fastq else "fasta", "hash": a.hash, "headers_only": not a.full,
                       "text_bytes": len(text), "out_bytes": len(out), "ms_per_step": dt * 1e3, "seqs_per_s": n / dt,
-                      "text_gbps": len(text) / dt / 1e9, "first_line": out[:80].split(b"\n")[0].decode()}))
+                      "text_gbps": len(text) / dt / 1e9, "device_ms": tp.last_ms(), "first_line": out[:80].tobytes().split(b"\n")[0].decode()}))
     tp.close()
 
 
