@@ -226,10 +226,15 @@ def main():
                  "frac_of_alu_pipe": (sha1_ach / probes["alu_pipe_lop3"]) if probes.get("alu_pipe_lop3") else None,
                  "probes_T": {k: (v / 1e12 if v else None) for k, v in probes.items()}, "theoretical_issue_T": theo / 1e12,
                  "work": f"{SHA1_INSTR_PER_BLOCK} int ops x {blocks_per_rec} blocks x {n} records per launch",
-                 "hbm_gbps": alg_bytes_sha1 / (ms_sha1 * 1e-3) / 1e9, "traffic": None, "kernel": "hash_tile_kernel<sha1>"}
+                 "hbm_gbps": alg_bytes_sha1 / (ms_sha1 * 1e-3) / 1e9,
+                 "traffic": (2_580_100_000 + 197_600_256) if n == N_RECORDS else None,
+                 "traffic_source": "ncu --set full, profiles/r01_sha1_tile.summary.txt: dram read 2.580 GB + write 0.198 GB per launch "
+                                   "(algorithmic: %.3f GB)" % (alg_bytes_sha1 / 1e9),
+                 "kernel": "hash_tile_kernel<sha1, upper, strip>"}
     xxh3_gbps = alg_bytes_xxh3 / (ms_xxh3 * 1e-3) / 1e9
     roof_xxh3 = {"bound": "hbm", "achieved": xxh3_gbps, "peak": hbm_peak, "unit": "GB/s", "frac": xxh3_gbps / hbm_peak,
-                 "peak_source": peak_src, "traffic": None, "kernel": "hash_tile_kernel<xxh3>",
+                 "peak_source": peak_src, "traffic": (2_580_072_000 + 80_899_328) if n == N_RECORDS else None,
+                 "traffic_source": "ncu --set full, profiles/r01_xxh3_tile.summary.txt", "kernel": "hash_tile_kernel<xxh3, upper, strip>",
                  "bytes": f"{alg_bytes_xxh3} algorithmic bytes per launch (residues + 8 B offsets + 8 B digest per record)"}
 
     # ---- e2e through the C ABI with host buffers ----
@@ -272,6 +277,38 @@ def main():
         for b in batches:
             b.close()
 
+    # ---- the whole record loop (split + strip + upper + hash + header rewrite + format) from TEXT, end to end ----
+    e2e_text = None
+    if not args.no_e2e:
+        try:
+            n_t = min(n, 4_000_000)
+            base = 20_000
+            seqs = d_res[: base * L].cpu().numpy().reshape(base, L)
+            block = b"".join(b">seq_%07d\n" % k + seqs[k].tobytes() + b"\n" for k in range(base))
+            text = block * (n_t // base)
+            n_t = base * (n_t // base)
+            tp = B.TextProc(len(text) + 1024, device=local)
+            tp.input[: len(text)] = np.frombuffer(text, dtype=np.uint8)
+            ids = [B.algo_id("sha1")]
+            for _ in range(2):
+                out_t, consumed, nrec, _ = tp.run(len(text), B.FORMAT_FASTA, True, ids, B.FLAG_UPPER, True, b"big.fasta")
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                out_t, consumed, nrec, _ = tp.run(len(text), B.FORMAT_FASTA, True, ids, B.FLAG_UPPER, True, b"big.fasta")
+            dt = time.perf_counter() - t0
+            barrier()
+            dt = max_over_ranks(dt) / args.steps
+            e2e_text = {"value": n_t * world / dt, "unit": "seqs/s", "ms_per_step": dt * 1e3, "text_gbps": len(text) * world / dt / 1e9,
+                        "h2d_bytes_per_step": len(text) * world, "d2h_bytes_per_step": int(out_t.size) * world,
+                        "records_per_gpu": nrec, "device_ms": tp.last_ms(),
+                        "api": "shb_textproc_run: single-line FASTA text in pinned host memory -> `file;sha1;name` lines in host "
+                               "memory (--headersonly); replaces the whole loop body seqhasher.go:227-283",
+                        "first_line": out_t[:64].tobytes().split(b"\n")[0].decode()}
+            tp.close()
+        except Exception as ex:   # keep the headline line even if this extra leg fails
+            e2e_text = {"error": str(ex)}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -302,7 +339,7 @@ def main():
                 "roofline": roof_sha1,
                 "xxh3": {"value": n * world / (ms_xxh3 * 1e-3), "unit": "seqs/s", "ms_per_step": ms_xxh3,
                          "gbps": n * world * L / (ms_xxh3 * 1e-3) / 1e9, "roofline": roof_xxh3, "clocks": clocks_x},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "cpu_baseline": cpu, "e2e": e2e, "e2e_text": e2e_text, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
