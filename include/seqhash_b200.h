@@ -42,6 +42,10 @@ enum shb_algo {
 #define SHB_FLAG_UPPER 1u     /* ASCII a-z -> A-Z: seqhasher.go:249-251 (set unless --casesensitive) */
 #define SHB_FLAG_STRIP 2u     /* drop \t \n \v \f \r ' ': seqhasher.go:246 */
 #define SHB_FLAG_EMIT_SEQ 4u  /* also return the normalised sequences (record.Seq.Seq = seq, :252) */
+/* Path override for cross-checking (tests): the library normally picks the kernel family from the mean record
+ * length; these force the thread-per-record direct kernels / forbid the long-record kernels. */
+#define SHB_FLAG_FORCE_DIRECT 0x100u
+#define SHB_FLAG_NO_LONG_PATH 0x200u
 
 /* Error codes. */
 #define SHB_OK 0

@@ -20,6 +20,8 @@ DIGEST_SIZES = [20, 64, 16, 8, 8, 16, 16, 8, 32, 128, 8, 4]
 FLAG_UPPER = 1
 FLAG_STRIP = 2
 FLAG_EMIT_SEQ = 4
+FLAG_FORCE_DIRECT = 0x100
+FLAG_NO_LONG_PATH = 0x200
 
 # every symbol include/seqhash_b200.h declares (tests check the library exports all of them)
 EXPORTS = [

@@ -69,7 +69,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
     // thread per record straight from global memory, or the long-record kernels (mean >= 2 KiB).
     const size_t mean = n ? total_bytes / n : 0;
     const size_t tile_need = (mean * 128 * 5 / 4 + 1024 + 1023) / 1024 * 1024;
-    const bool tile_mode = n && tile_need <= 100 * 1024;
+    const bool tile_mode = n && tile_need <= 100 * 1024 && !(flags & SHB_FLAG_FORCE_DIRECT);
     const bool prepass = emit || (strip && !tile_mode);   // materialise the normalised batch first
     uint8_t *fused_strip_scratch = nullptr;
     int64_t *fused_out_len = nullptr;
@@ -119,7 +119,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
                                      d_out_len, static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).scan_off, st));
     } else {
         // mean >= 2 KiB: the hashes with parallelism inside a record leave the thread-per-record path
-        const bool long_mode = n && mean >= 2048;
+        const bool long_mode = n && mean >= 2048 && !(flags & (SHB_FLAG_FORCE_DIRECT | SHB_FLAG_NO_LONG_PATH));
         for (int a = 0; a < SHB_N_ALGOS; a++) {
             if (!(want >> a & 1u)) continue;
             if (long_mode && a == SHB_NTHASH) {
