@@ -27,6 +27,14 @@ size_t sho_digest_size(int algo) { return (algo >= 0 && algo < SHO_N_ALGOS) ? al
 /* ---- optional tuned back-ends for the CPU-baseline timing (same results) ---- */
 
 typedef unsigned char *(*ossl_oneshot_fn)(const unsigned char *, size_t, unsigned char *);
+/* low-level (deprecated but present) init/update/final: unlike the one-shot SHA1()/MD5() of OpenSSL 3 they
+ * do not fetch the algorithm under a global lock on every call, so they scale across threads */
+typedef int (*ossl_init_fn)(void *);
+typedef int (*ossl_update_fn)(void *, const void *, size_t);
+typedef int (*ossl_final_fn)(unsigned char *, void *);
+static ossl_init_fn sha1_init, md5_init;
+static ossl_update_fn sha1_update, md5_update;
+static ossl_final_fn sha1_final, md5_final;
 typedef int (*evp_q_digest_fn)(void *, const char *, const char *, const void *, size_t, unsigned char *,
                                size_t *);
 typedef uint64_t (*xxh64_fn)(const void *, size_t, uint64_t);
@@ -46,7 +54,15 @@ static void accel_load(void)
         ossl_sha1 = (ossl_oneshot_fn)dlsym(c, "SHA1");
         ossl_md5 = (ossl_oneshot_fn)dlsym(c, "MD5");
         ossl_q_digest = (evp_q_digest_fn)dlsym(c, "EVP_Q_digest");
-        if (ossl_sha1 && ossl_md5 && ossl_q_digest) accel_state |= 1;
+        sha1_init = (ossl_init_fn)dlsym(c, "SHA1_Init");
+        sha1_update = (ossl_update_fn)dlsym(c, "SHA1_Update");
+        sha1_final = (ossl_final_fn)dlsym(c, "SHA1_Final");
+        md5_init = (ossl_init_fn)dlsym(c, "MD5_Init");
+        md5_update = (ossl_update_fn)dlsym(c, "MD5_Update");
+        md5_final = (ossl_final_fn)dlsym(c, "MD5_Final");
+        if (ossl_sha1 && ossl_md5 && ossl_q_digest && sha1_init && sha1_update && sha1_final && md5_init && md5_update &&
+            md5_final)
+            accel_state |= 1;
     }
     void *x = dlopen("libxxhash.so.0", RTLD_NOW | RTLD_LOCAL);
     if (x) {
@@ -70,14 +86,24 @@ static size_t hash_dispatch(int algo, const uint8_t *data, size_t len, uint8_t *
     uint64_t a, b;
     switch (algo) {
     case SHO_SHA1:
-        if (accel & 1) ossl_sha1(data, len, out); else sho_sha1(data, len, out);
+        if (accel & 1) {
+            uint64_t ctx[32];   /* SHA_CTX is 96 bytes */
+            sha1_init(ctx); sha1_update(ctx, data, len); sha1_final(out, ctx);
+        } else {
+            sho_sha1(data, len, out);
+        }
         return 20;
     case SHO_SHA3:
         if (accel & 1) { size_t ol = 64; ossl_q_digest(NULL, "SHA3-512", NULL, data, len, out, &ol); }
         else sho_sha3_512(data, len, out);
         return 64;
     case SHO_MD5:
-        if (accel & 1) ossl_md5(data, len, out); else sho_md5(data, len, out);
+        if (accel & 1) {
+            uint64_t ctx[32];   /* MD5_CTX is 92 bytes */
+            md5_init(ctx); md5_update(ctx, data, len); md5_final(out, ctx);
+        } else {
+            sho_md5(data, len, out);
+        }
         return 16;
     case SHO_XXHASH: /* fmt "%016x" */
         store_be64(out, (accel & 2) ? lib_xxh64(data, len, 0) : sho_xxh64(data, len));

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libseqhash_b200.so")
+LIB_PATH = os.environ.get("SHB_LIB") or os.path.join(_PKG, "libseqhash_b200.so")   # SHB_LIB: A/B-test another build
 
 ALGO_NAMES = ["sha1", "sha3", "md5", "xxhash", "xxh3", "cityhash", "murmur3", "nthash", "blake3", "k12",
               "rapidhash", "rapidhash32"]

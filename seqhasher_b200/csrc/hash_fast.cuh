@@ -83,7 +83,7 @@ __device__ __forceinline__ uint64_t xxh64_record(const R &r, uint32_t len)
 
 // default 192-byte secret of XXH3 (kSecret), as 64-bit LE words at byte offsets 0,8,..,184 plus the
 // unaligned views the algorithm needs (offsets 3, 11, 19, .. and 119, 121, 127).
-__constant__ uint8_t c_xxh3_secret[192 + 8] = {
+__constant__ __align__(16) uint8_t c_xxh3_secret[192 + 8] = {
     0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
     0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
     0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
