@@ -68,7 +68,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
     // residues are read once, and the whitespace strip is fused into the tile pass.  Longer records: one
     // thread per record straight from global memory, or the long-record kernels (mean >= 2 KiB).
     const size_t mean = n ? total_bytes / n : 0;
-    const size_t tile_need = (mean * 128 * 5 / 4 + 1024 + 1023) / 1024 * 1024;
+    const size_t tile_need = (mean * 128 * 17 / 16 + 1024 + 1023) / 1024 * 1024;   // 6 % slack + 1 KiB: oversize tiles fall back per CTA
     const bool tile_mode = n && tile_need <= 100 * 1024 && !(flags & SHB_FLAG_FORCE_DIRECT);
     const bool prepass = emit || (strip && !tile_mode);   // materialise the normalised batch first
     uint8_t *fused_strip_scratch = nullptr;
