@@ -126,6 +126,10 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
                 CU(shb::launch_nthash_long(fused_upper, res, offs, n, slot_of[a], st));
             } else if (long_mode && a == SHB_XXH3) {
                 CU(shb::launch_xxh3_long(fused_upper, res, offs, n, slot_of[a], st));
+            } else if (long_mode && a == SHB_K12 && d_scratch) {
+                ScratchLayout L(total_bytes, n);
+                CU(shb::launch_k12_long(fused_upper, res, offs, n, total_bytes, slot_of[a],
+                                        static_cast<uint8_t *>(d_scratch) + L.b3_off, st));
             } else if (long_mode && a == SHB_BLAKE3 && d_scratch) {
                 ScratchLayout L(total_bytes, n);
                 CU(shb::launch_blake3_long(fused_upper, res, offs, n, total_bytes, slot_of[a],
@@ -214,7 +218,7 @@ int shb_algo_id(const char *name)
 const char *shb_algo_name(int algo) { return (algo >= 0 && algo < SHB_N_ALGOS) ? kNames[algo] : nullptr; }
 size_t shb_digest_size(int algo) { return (algo >= 0 && algo < SHB_N_ALGOS) ? (size_t)shb::digest_size(algo) : 0; }
 
-unsigned long long shb_launch_count(void) { return shb::g_launches; }
+unsigned long long shb_launch_count(void) { return shb::g_launches.load(); }
 
 size_t shb_scratch_bytes(size_t total_bytes, size_t n_records) { return ScratchLayout(total_bytes, n_records).total; }
 
@@ -297,7 +301,7 @@ int shb_submit(shb_batch *b, size_t n, const int *algos, int n_algos, unsigned f
     }
     const bool norm = flags & (SHB_FLAG_STRIP | SHB_FLAG_EMIT_SEQ);
     bool wants_b3_long = false;
-    for (int k = 0; k < n_algos; k++) wants_b3_long |= (algos[k] == SHB_BLAKE3 && n && total / n >= 2048);
+    for (int k = 0; k < n_algos; k++) wants_b3_long |= ((algos[k] == SHB_BLAKE3 || algos[k] == SHB_K12) && n && total / n >= 2048);
     if (norm || wants_b3_long) {
         const size_t sneed = ScratchLayout(b->max_bytes, b->max_records).total;
         if (sneed > b->scratch_cap) {

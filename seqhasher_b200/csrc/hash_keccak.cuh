@@ -165,8 +165,26 @@ __device__ __forceinline__ void kt128_record(const R &r, uint32_t len, uint8_t *
 // final node = S_0 || 03 00.. (8 B) || CV_1.. || length_encode(n-1) || FF FF, suffix 0x06.
 // The final node's pending rate block is kept as 21 lanes in local memory because the lane
 // position of each CV depends on the chunk index.
+
+// chaining value of leaf chunk c (>= 1) of a record of `len` bytes
 template <class R>
-__device__ __noinline__ void kt128_long(const R &r, uint32_t len, uint8_t *out)
+__device__ __forceinline__ void kt128_leaf_cv(const R &r, uint32_t len, uint32_t c, uint64_t (&cv)[4])
+{
+    const uint32_t slen = len + 1;
+    const uint32_t start = c << 13;
+    const uint32_t clen = min(8192u, slen - start);        // chunk length within S
+    const uint32_t dlen = min(clen, len - start);          // message bytes in it
+    uint64_t a[25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) a[i] = 0;
+    sponge_absorb_padded<21, 12>(a, r, start, dlen, clen, 0x0Bu);
+#pragma unroll
+    for (int j = 0; j < 4; j++) cv[j] = a[j];
+}
+
+// final node; leaf CVs come from `leaf(c, cv)` (computed inline, or read back from the leaf kernel's output)
+template <class R, class LeafFn>
+__device__ __forceinline__ void kt128_final_node(const R &r, uint32_t len, uint8_t *out, LeafFn leaf)
 {
     uint64_t f[25];
 #pragma unroll
@@ -185,13 +203,8 @@ __device__ __noinline__ void kt128_long(const R &r, uint32_t len, uint8_t *out)
     const uint32_t slen = len + 1;
     const uint32_t n = (slen + 8191) >> 13;
     for (uint32_t c = 1; c < n; c++) {
-        const uint32_t start = c << 13;
-        const uint32_t clen = min(8192u, slen - start);        // chunk length within S
-        const uint32_t dlen = min(clen, len - start);          // message bytes in it
-        uint64_t a[25];
-#pragma unroll
-        for (int i = 0; i < 25; i++) a[i] = 0;
-        sponge_absorb_padded<21, 12>(a, r, start, dlen, clen, 0x0Bu);
+        uint64_t cv[4];
+        leaf(c, cv);
 #pragma unroll 1
         for (int j = 0; j < 4; j++) {
             if (pos == 21) {
@@ -200,7 +213,7 @@ __device__ __noinline__ void kt128_long(const R &r, uint32_t len, uint8_t *out)
                 keccak_p<12>(f);
                 pos = 0;
             }
-            pend[pos++] = a[j];
+            pend[pos++] = cv[j];
         }
     }
     // trailer: length_encode(n-1) || FF FF, then the 0x06 suffix; n-1 < 2^24 here
@@ -226,6 +239,12 @@ __device__ __noinline__ void kt128_long(const R &r, uint32_t len, uint8_t *out)
     uint64_t *o = reinterpret_cast<uint64_t *>(out);
 #pragma unroll
     for (int i = 0; i < 16; i++) o[i] = f[i];
+}
+
+template <class R>
+__device__ __noinline__ void kt128_long(const R &r, uint32_t len, uint8_t *out)
+{
+    kt128_final_node(r, len, out, [&](uint32_t c, uint64_t (&cv)[4]) { kt128_leaf_cv(r, len, c, cv); });
 }
 
 }  // namespace shb

@@ -12,7 +12,7 @@
 
 namespace shb {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 template <int ALGO, bool UPPER>
 __global__ void __launch_bounds__(128) hash_direct_kernel(const uint8_t *__restrict__ res,

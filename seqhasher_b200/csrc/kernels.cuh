@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <atomic>
 #include <cuda_runtime.h>
 
 namespace shb {
@@ -17,7 +18,7 @@ __host__ __device__ constexpr int digest_size(int a)
     return S[a];
 }
 
-extern unsigned long long g_launches;   // kernels launched by this library (host counter)
+extern std::atomic<unsigned long long> g_launches;   // kernels launched by this library (host counter)
 
 // Byte blocks of the normalise pre-pass.
 constexpr uint32_t NORM_BLK = 4096;
@@ -44,6 +45,10 @@ cudaError_t launch_nthash_long(bool upper, const uint8_t *res, const int64_t *of
                                cudaStream_t st);
 cudaError_t launch_xxh3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, uint8_t *out, cudaStream_t st);
 size_t b3_long_scratch_bytes(size_t total_bytes, size_t n);
+// K12 leaf-parallel: thread per 8 KiB leaf over the flattened leaf list + thread per record final node
+// (scratch: same layout/size as the BLAKE3 long path)
+cudaError_t launch_k12_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
+                            uint8_t *out, void *scratch, cudaStream_t st);
 cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
                                uint8_t *out, void *scratch, cudaStream_t st);
 

@@ -239,6 +239,102 @@ cudaError_t launch_xxh3_long(bool upper, const uint8_t *res, const int64_t *offs
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------- K12
+
+// leaves of record i = chunks 1.. of S = M || 0x00 (8192 bytes each); records of <= 8191 bytes have none
+__global__ void k12_count_leaves_kernel(const int64_t *__restrict__ offs, size_t n, uint32_t *__restrict__ counts)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t len = offs[i + 1] - offs[i];
+        counts[i] = len >= 8192 ? (uint32_t)(((len + 1 + 8191) >> 13) - 1) : 0u;
+    }
+}
+
+// One thread per leaf over the flattened leaf list of the batch: CV (32 bytes) to cvs[global leaf id].
+template <bool UPPER>
+__global__ void __launch_bounds__(128) k12_leaves_kernel(const uint8_t *__restrict__ res, const int64_t *__restrict__ offs,
+                                                         size_t n, const int64_t *__restrict__ leaf_base,
+                                                         uint64_t *__restrict__ cvs)
+{
+    const int64_t total = leaf_base[n];
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    size_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const size_t mid = (lo + hi) >> 1;
+        if (leaf_base[mid] <= g) lo = mid; else hi = mid;
+    }
+    const size_t i = lo;
+    const int64_t s = offs[i];
+    const uint32_t len = (uint32_t)(offs[i + 1] - s);
+    const uint32_t c = (uint32_t)(g - leaf_base[i]) + 1u;
+    GlobalReader<UPPER> r(res, s);
+    uint64_t cv[4];
+    kt128_leaf_cv(r, len, c, cv);
+    uint64_t *dst = cvs + g * 4;
+    *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(cv[0], cv[1]);
+    *reinterpret_cast<ulonglong2 *>(dst + 2) = make_ulonglong2(cv[2], cv[3]);
+}
+
+// One thread per record: the single-sponge form for short records, else the final node over S_0 and the
+// leaf CVs computed by k12_leaves_kernel.
+template <bool UPPER>
+__global__ void __launch_bounds__(128) k12_final_kernel(const uint8_t *__restrict__ res, const int64_t *__restrict__ offs,
+                                                        size_t n, const int64_t *__restrict__ leaf_base,
+                                                        const uint64_t *__restrict__ cvs, uint8_t *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t s = offs[i];
+    const uint32_t len = (uint32_t)(offs[i + 1] - s);
+    uint8_t *o = out + i * 128;
+    if (len == 0) {   // empty-sequence rule
+        zero_digest<A_K12>(o);
+        return;
+    }
+    GlobalReader<UPPER> r(res, s);
+    if (len < 8192) {
+        kt128_record(r, len, o);
+        return;
+    }
+    const uint64_t *my = cvs + leaf_base[i] * 4;
+    kt128_final_node(r, len, o, [&](uint32_t c, uint64_t (&cv)[4]) {
+        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(my + (size_t)(c - 1) * 4));
+        const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(my + (size_t)(c - 1) * 4 + 2));
+        cv[0] = a.x; cv[1] = a.y; cv[2] = b.x; cv[3] = b.y;
+    });
+}
+
+cudaError_t launch_k12_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
+                            uint8_t *out, void *scratch, cudaStream_t st)
+{
+    // scratch layout = the BLAKE3 one (counts, bases, 32-byte CVs, scan tmp): b3_long_scratch_bytes() covers it
+    if (n == 0) return cudaSuccess;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    uint8_t *base = static_cast<uint8_t *>(scratch);
+    uint32_t *counts = reinterpret_cast<uint32_t *>(base);
+    int64_t *leaf_base = reinterpret_cast<int64_t *>(base + up(n * sizeof(uint32_t)));
+    uint64_t *cvs = reinterpret_cast<uint64_t *>(base + up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)));
+    const size_t max_chunks0 = total_bytes / 1024 + n + 1;
+    void *scan_tmp = base + up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)) + up(max_chunks0 * 32);
+    k12_count_leaves_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(offs, n, counts);
+    g_launches++;
+    cudaError_t e = scan_counts(counts, n, leaf_base, scan_tmp, st);
+    if (e != cudaSuccess) return e;
+    const size_t max_leaves = total_bytes / 8192 + 1;
+    const unsigned blocks = (unsigned)((max_leaves + 127) / 128);
+    if (upper) {
+        k12_leaves_kernel<true><<<blocks, 128, 0, st>>>(res, offs, n, leaf_base, cvs);
+        k12_final_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(res, offs, n, leaf_base, cvs, out);
+    } else {
+        k12_leaves_kernel<false><<<blocks, 128, 0, st>>>(res, offs, n, leaf_base, cvs);
+        k12_final_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(res, offs, n, leaf_base, cvs, out);
+    }
+    g_launches += 2;
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------- BLAKE3
 
 // chunks of record i = max(1, ceil(len/1024)); written as uint32 counts for the shared scan kernel

@@ -70,7 +70,7 @@ def test_c3_20m_reads_fused(shb, oracle):
 
 
 def test_c4_long_reads(shb, oracle):
-    _check(shb, oracle, 20_000, (10_000, 50_000), ["blake3", "nthash", "xxh3"], 0, 0xC4, shb.FLAG_NO_LONG_PATH)
+    _check(shb, oracle, 20_000, (10_000, 50_000), ["blake3", "nthash", "xxh3", "k12"], 0, 0xC4, shb.FLAG_NO_LONG_PATH)
 
 
 def test_c5_variable_all_algorithms(shb, oracle):
