@@ -223,6 +223,7 @@ __device__ __forceinline__ void murmur3_record(const R &r, uint32_t len, uint64_
     const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
     uint64_t h1 = 0, h2 = 0;
     const uint32_t nblocks = len >> 4;
+#pragma unroll 4
     for (uint32_t i = 0; i < nblocks; i++) {
         uint64_t k1 = r.u64(16 * i), k2 = r.u64(16 * i + 8);
         k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;

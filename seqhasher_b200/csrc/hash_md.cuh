@@ -92,7 +92,7 @@ __device__ __forceinline__ uint32_t md_tail_word(const R &r, uint32_t off, uint3
 // out: 20 bytes, 4-byte aligned
 // (The branch-free md_tail_word form measured 8 % slower here when the reader also carries the whitespace
 // detector — the kernel runs at 20 warps/SM and the longer dependent chains of the tail stall it — so SHA-1
-// keeps the predicated padded_u32 tail; MD5 below is 7 % faster with md_tail_word.  A/B: _cmp/quick.py.)
+// keeps the predicated padded_u32 tail; MD5 below is 7 % faster with md_tail_word.  A/B: tools/ab_quick.py.)
 template <class R>
 __device__ __forceinline__ void sha1_record(const R &r, uint32_t len, uint8_t *out)
 {
@@ -142,6 +142,8 @@ __device__ __forceinline__ void md5_compress(uint32_t (&h)[4], const uint32_t (&
         else { f = c ^ (b | ~d); g = (7 * i) & 15; }
         uint32_t t = d;
         d = c; c = b;
+        // (forcing these adds onto the FMA pipe, as in SHA-1, measured 15 % slower: MD5 is one serial chain and
+        //  the cross-pipe hop adds latency to every step)
         b = b + rotl32(a + f + K[i] + m[g], S[i >> 4][i & 3]);
         a = t;
     }
