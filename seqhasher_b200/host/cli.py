@@ -158,4 +158,9 @@ def main(argv: list[str] | None = None) -> int:
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    import os
+    code = main()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    # skip interpreter / CUDA teardown: unpinning and freeing the staging buffers costs ~1 s and the OS does it anyway
+    os._exit(code)

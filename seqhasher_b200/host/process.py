@@ -95,12 +95,19 @@ def process_sequences_gpu(input_stream, output_stream, cfg, textproc=None, chunk
         eof = False
         while True:
             while not eof and fill < tp.capacity:
-                chunk = f.read(tp.capacity - fill)
-                if not chunk:
-                    eof = True
-                    break
-                tp.input[fill: fill + len(chunk)] = memoryview(chunk)
-                fill += len(chunk)
+                if hasattr(f, "readinto"):      # straight into the pinned buffer: no intermediate bytes object
+                    got = f.readinto(memoryview(tp.input)[fill: tp.capacity])
+                    if not got:
+                        eof = True
+                        break
+                    fill += got
+                else:
+                    chunk = f.read(tp.capacity - fill)
+                    if not chunk:
+                        eof = True
+                        break
+                    tp.input[fill: fill + len(chunk)] = memoryview(chunk)
+                    fill += len(chunk)
             if fmt == 0:
                 # sniff: skip leading blank space, first byte decides (fastx.NewReaderFromIO, seqhasher.go:221)
                 head = bytes(tp.input[:fill])

@@ -1,0 +1,70 @@
+"""The reference's own published benchmark (README.md:156-236), run end to end through THIS
+repo's CLI: 500 000 random-ACGT single-line FASTA records, length uniform 30-3000 (~760 MB),
+`seqhasher --headersonly --casesensitive --hash X big.fasta - > /dev/null`, wall time of the whole process
+(interpreter start, CUDA init, file read, GPU record loop, write to /dev/null).
+usage: python tools/bench_readme_cli.py [--runs 3]"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+README_S = {"md5": 1.712, "sha1": 1.614, "sha3": 4.823, "xxhash": 0.977, "murmur3": 1.106, "cityhash": 1.078, "nthash": 2.138,
+            "blake3": 1.718, "sha1,blake3": 3.384, "xxhash,murmur3": 2.234}
+
+
+def make_file(path, n=500_000, seed=42):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(30, 3001, size=n)
+    total = int(lens.sum())
+    seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=total).tobytes()
+    with open(path, "wb") as f:
+        pos = 0
+        parts = []
+        for i, L in enumerate(lens):
+            parts.append(b">seq_%d\n" % (i + 1))
+            parts.append(seq[pos:pos + L])
+            parts.append(b"\n")
+            pos += L
+            if len(parts) > 30000:
+                f.write(b"".join(parts)); parts = []
+        f.write(b"".join(parts))
+    return total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--runs", type=int, default=3)
+    a = ap.parse_args()
+    path = "/tmp/big.fasta"
+    bp = make_file(path)
+    size = os.path.getsize(path)
+    rows = []
+    for hashes, ref_s in README_S.items():
+        cs = [] if "," in hashes else ["--casesensitive"]     # the two multi-hash rows of the README omit it
+        cmd = [sys.executable, "-m", "seqhasher_b200.host.cli", "--headersonly", *cs, "--hash", hashes, path, "-"]
+        times = []
+        for r in range(a.runs + 1):                            # first run warms the page cache / CUDA driver
+            t0 = time.perf_counter()
+            with open(os.devnull, "wb") as dn:
+                subprocess.run(cmd, cwd=ROOT, stdout=dn, check=True)
+            if r:
+                times.append(time.perf_counter() - t0)
+        mean = sum(times) / len(times)
+        rows.append({"hash": hashes, "mean_s": mean, "min_s": min(times), "k_seqs_per_s": 500 / mean, "MB_per_s": bp / mean / 1e6,
+                     "reference_readme_s": ref_s, "ratio_vs_readme": ref_s / mean})
+        print(json.dumps(rows[-1]), flush=True)
+    out = {"what": "reference README benchmark through `python -m seqhasher_b200.host.cli` (whole process wall time)",
+           "file_bytes": size, "bp": bp, "runs": a.runs, "rows": rows,
+           "note": "README numbers: Intel i7-10510U laptop, Go binary; here: B200 box, Python host + GPU record loop"}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "readme_cli_bench.json"), "w"), indent=1)
+    os.remove(path)
+
+
+if __name__ == "__main__":
+    main()
