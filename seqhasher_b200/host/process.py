@@ -146,7 +146,14 @@ def process_sequences_gpu(input_stream, output_stream, cfg, textproc=None, chunk
             if eof:
                 return
             if consumed == 0:
-                raise RuntimeError("Error reading record: record larger than the GPU text buffer")
+                # one record does not fit the text buffer (e.g. a chromosome): grow the buffer and retry
+                if not own or tp.capacity >= (1 << 31):
+                    raise RuntimeError("Error reading record: record larger than the GPU text buffer")
+                bigger = B.TextProc(min(tp.capacity * 4, 1 << 31))
+                bigger.input[:fill] = tp.input[:fill]
+                tp.close()
+                tp = bigger
+                continue
             rest = fill - consumed
             if rest:
                 tp.input[:rest] = tp.input[consumed:fill].copy()

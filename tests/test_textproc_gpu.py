@@ -178,3 +178,14 @@ def test_large_text_uses_tiled_scans(H, oracle):
     assert len(fq) > 17 << 20
     got = run_gpu(H, fq, cfg, chunk=32 << 20)
     assert got == expected(oracle, fq, cfg)
+
+
+def test_record_larger_than_chunk_grows_buffer(H, oracle):
+    # a 300 kB record with a 64 kB text buffer: the host loop must grow the buffer instead of failing
+    rng = np.random.default_rng(5)
+    big = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=300_000).tobytes()
+    data = b">small\nACGT\n>chrBig some description\n" + b"\n".join(big[i:i + 70] for i in range(0, len(big), 70)) + b"\n>tail\nTTGA\n"
+    cfg = H.Config(hash_types=["sha1", "blake3"], headers_only=True, input_file_name="g.fa")
+    out = io.BytesIO()
+    H.process_sequences_gpu(io.BytesIO(data), out, cfg, chunk_bytes=1 << 16, log=io.StringIO())
+    assert out.getvalue() == expected(oracle, data, cfg)
