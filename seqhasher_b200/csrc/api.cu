@@ -63,7 +63,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
     const uint8_t *res = d_res;
     const int64_t *offs = d_offs;
     bool fused_upper = upper;
-    // Path choice.  Short records (mean <= 640 B): shared-memory tiles of 128 records, sized so that at
+    // Path choice.  Short records (mean <= ~740 B): shared-memory tiles of 128 records, sized so that at
     // least two CTAs fit per SM; the HBM-bound hashes requested together are fused into one launch so the
     // residues are read once, and the whitespace strip is fused into the tile pass.  Longer records: one
     // thread per record straight from global memory, or the long-record kernels (mean >= 2 KiB).
