@@ -46,6 +46,7 @@ enum shb_algo {
  * length; these force the thread-per-record direct kernels / forbid the long-record kernels. */
 #define SHB_FLAG_FORCE_DIRECT 0x100u
 #define SHB_FLAG_NO_LONG_PATH 0x200u
+#define SHB_FLAG_NO_LENGTH_SORT 0x400u   /* thread-per-record kernels in input order instead of length order */
 
 /* Error codes. */
 #define SHB_OK 0

@@ -22,6 +22,7 @@ FLAG_STRIP = 2
 FLAG_EMIT_SEQ = 4
 FLAG_FORCE_DIRECT = 0x100
 FLAG_NO_LONG_PATH = 0x200
+FLAG_NO_LENGTH_SORT = 0x400
 
 # every symbol include/seqhash_b200.h declares (tests check the library exports all of them)
 EXPORTS = [

@@ -14,13 +14,16 @@ namespace shb {
 
 std::atomic<unsigned long long> g_launches{0};
 
+// perm (may be null): records in descending length order, so the 32 records of a warp need about the same
+// number of blocks; digests are still written at the record's own index (input order).
 template <int ALGO, bool UPPER>
 __global__ void __launch_bounds__(128) hash_direct_kernel(const uint8_t *__restrict__ res,
                                                           const int64_t *__restrict__ offs, size_t n,
-                                                          uint8_t *__restrict__ out)
+                                                          uint8_t *__restrict__ out, const uint32_t *__restrict__ perm)
 {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        const size_t i = perm ? (size_t)perm[t] : t;
         const int64_t s = offs[i], e = offs[i + 1];
         const uint32_t len = (uint32_t)(e - s);
         uint8_t *o = out + i * digest_size(ALGO);
@@ -35,36 +38,101 @@ __global__ void __launch_bounds__(128) hash_direct_kernel(const uint8_t *__restr
 
 template <int ALGO>
 static cudaError_t launch_direct_t(bool upper, const uint8_t *res, const int64_t *offs, size_t n, uint8_t *out,
-                                   cudaStream_t st)
+                                   const uint32_t *perm, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     const int threads = 128;
     size_t blocks = (n + threads - 1) / threads;
     if (blocks > 148u * 64u) blocks = 148u * 64u;
-    if (upper) hash_direct_kernel<ALGO, true><<<(unsigned)blocks, threads, 0, st>>>(res, offs, n, out);
-    else hash_direct_kernel<ALGO, false><<<(unsigned)blocks, threads, 0, st>>>(res, offs, n, out);
+    if (upper) hash_direct_kernel<ALGO, true><<<(unsigned)blocks, threads, 0, st>>>(res, offs, n, out, perm);
+    else hash_direct_kernel<ALGO, false><<<(unsigned)blocks, threads, 0, st>>>(res, offs, n, out, perm);
     g_launches++;
     return cudaGetLastError();
 }
 
 cudaError_t launch_hash_direct(int algo, bool upper, const uint8_t *res, const int64_t *offs, size_t n,
-                               uint8_t *out, cudaStream_t st)
+                               uint8_t *out, const uint32_t *perm, cudaStream_t st)
 {
     switch (algo) {
-    case A_SHA1: return launch_direct_t<A_SHA1>(upper, res, offs, n, out, st);
-    case A_SHA3: return launch_direct_t<A_SHA3>(upper, res, offs, n, out, st);
-    case A_MD5: return launch_direct_t<A_MD5>(upper, res, offs, n, out, st);
-    case A_XXHASH: return launch_direct_t<A_XXHASH>(upper, res, offs, n, out, st);
-    case A_XXH3: return launch_direct_t<A_XXH3>(upper, res, offs, n, out, st);
-    case A_CITYHASH: return launch_direct_t<A_CITYHASH>(upper, res, offs, n, out, st);
-    case A_MURMUR3: return launch_direct_t<A_MURMUR3>(upper, res, offs, n, out, st);
-    case A_NTHASH: return launch_direct_t<A_NTHASH>(upper, res, offs, n, out, st);
-    case A_BLAKE3: return launch_direct_t<A_BLAKE3>(upper, res, offs, n, out, st);
-    case A_K12: return launch_direct_t<A_K12>(upper, res, offs, n, out, st);
-    case A_RAPIDHASH: return launch_direct_t<A_RAPIDHASH>(upper, res, offs, n, out, st);
-    case A_RAPIDHASH32: return launch_direct_t<A_RAPIDHASH32>(upper, res, offs, n, out, st);
+    case A_SHA1: return launch_direct_t<A_SHA1>(upper, res, offs, n, out, perm, st);
+    case A_SHA3: return launch_direct_t<A_SHA3>(upper, res, offs, n, out, perm, st);
+    case A_MD5: return launch_direct_t<A_MD5>(upper, res, offs, n, out, perm, st);
+    case A_XXHASH: return launch_direct_t<A_XXHASH>(upper, res, offs, n, out, perm, st);
+    case A_XXH3: return launch_direct_t<A_XXH3>(upper, res, offs, n, out, perm, st);
+    case A_CITYHASH: return launch_direct_t<A_CITYHASH>(upper, res, offs, n, out, perm, st);
+    case A_MURMUR3: return launch_direct_t<A_MURMUR3>(upper, res, offs, n, out, perm, st);
+    case A_NTHASH: return launch_direct_t<A_NTHASH>(upper, res, offs, n, out, perm, st);
+    case A_BLAKE3: return launch_direct_t<A_BLAKE3>(upper, res, offs, n, out, perm, st);
+    case A_K12: return launch_direct_t<A_K12>(upper, res, offs, n, out, perm, st);
+    case A_RAPIDHASH: return launch_direct_t<A_RAPIDHASH>(upper, res, offs, n, out, perm, st);
+    case A_RAPIDHASH32: return launch_direct_t<A_RAPIDHASH32>(upper, res, offs, n, out, perm, st);
     default: return cudaErrorInvalidValue;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Length binning for the thread-per-record kernels: a counting sort of the record indices by
+// ceil(len / 64) (descending), so that a warp's 32 records finish together.  Thread-per-record over
+// 30-3000-byte records otherwise runs every warp for its longest record (about half the lanes idle).
+constexpr uint32_t LEN_BUCKETS = 4096;   // 64-byte granularity up to 256 KiB, longer records share the first bucket
+
+__device__ __forceinline__ uint32_t len_bucket(int64_t len)
+{
+    const int64_t b = (len + 63) >> 6;
+    return (LEN_BUCKETS - 1) - (uint32_t)(b < (int64_t)LEN_BUCKETS - 1 ? b : (int64_t)LEN_BUCKETS - 1);   // long first
+}
+
+__global__ void __launch_bounds__(256) len_hist_kernel(const int64_t *__restrict__ offs, size_t n, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t s_h[LEN_BUCKETS];
+    for (uint32_t k = threadIdx.x; k < LEN_BUCKETS; k += blockDim.x) s_h[k] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&s_h[len_bucket(offs[i + 1] - offs[i])], 1u);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < LEN_BUCKETS; k += blockDim.x)
+        if (s_h[k]) atomicAdd(&hist[k], s_h[k]);
+}
+
+__global__ void __launch_bounds__(1024) len_scan_kernel(uint32_t *__restrict__ hist)   // in place: counts -> cursors
+{
+    __shared__ uint32_t s[LEN_BUCKETS];
+    for (uint32_t k = threadIdx.x; k < LEN_BUCKETS; k += 1024) s[k] = hist[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t k = 0; k < LEN_BUCKETS; k++) { const uint32_t c = s[k]; s[k] = run; run += c; }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < LEN_BUCKETS; k += 1024) hist[k] = s[k];
+}
+
+__global__ void __launch_bounds__(256) len_scatter_kernel(const int64_t *__restrict__ offs, size_t n,
+                                                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ perm)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        perm[atomicAdd(&cursor[len_bucket(offs[i + 1] - offs[i])], 1u)] = (uint32_t)i;
+}
+
+size_t length_sort_bytes(size_t n) { return (n * 4 + 255) / 256 * 256 + LEN_BUCKETS * 4; }
+
+// perm_and_tmp: length_sort_bytes(n) bytes; perm = first n uint32
+cudaError_t launch_length_sort(const int64_t *offs, size_t n, void *perm_and_tmp, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    uint32_t *perm = static_cast<uint32_t *>(perm_and_tmp);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(perm_and_tmp) + (n * 4 + 255) / 256 * 256);
+    cudaError_t e = cudaMemsetAsync(hist, 0, LEN_BUCKETS * 4, st);
+    if (e != cudaSuccess) return e;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    len_hist_kernel<<<(unsigned)blocks, 256, 0, st>>>(offs, n, hist);
+    len_scan_kernel<<<1, 1024, 0, st>>>(hist);
+    len_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(offs, n, hist, perm);
+    g_launches += 3;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

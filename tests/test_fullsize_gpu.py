@@ -75,4 +75,4 @@ def test_c4_long_reads(shb, oracle):
 
 def test_c5_variable_all_algorithms(shb, oracle):
     from seqhasher_b200.binding import ALGO_NAMES
-    _check(shb, oracle, 300_000, (30, 3000), ALGO_NAMES, 3, 0xC5, shb.FLAG_FORCE_DIRECT, sample=3000)
+    _check(shb, oracle, 300_000, (30, 3000), ALGO_NAMES, 3, 0xC5, shb.FLAG_NO_LENGTH_SORT, sample=3000)
