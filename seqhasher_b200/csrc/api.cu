@@ -120,11 +120,17 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
                                      d_out_len, static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).scan_off, st));
     } else {
         // mean >= 2 KiB: the hashes with parallelism inside a record leave the thread-per-record path
-        const bool long_mode = n && mean >= 2048 && !(flags & (SHB_FLAG_FORCE_DIRECT | SHB_FLAG_NO_LONG_PATH));
+        // Kernels with parallelism inside a record.  The warp-per-record ones (ntHash 3.7x, XXH3 1.8x faster than
+        // thread-per-record already at 1.5 kB) take over as soon as tiles no longer fit; the chunk-/leaf-parallel
+        // BLAKE3 and K12 only pay off for multi-kilobyte records (below, the length-sorted direct kernels win).
+        const bool long_ok = n && !(flags & (SHB_FLAG_FORCE_DIRECT | SHB_FLAG_NO_LONG_PATH));
+        const bool long_mode = long_ok && mean >= 4096;
         // The INT-bound thread-per-record kernels walk the records in descending length order so a warp's 32
         // records finish together (sha1 +49 %, sha3 +85 %, blake3 +52 %, k12 +86 % on 30-3000-byte records);
         // the memory-bound hashes keep input order: for them the lost locality costs more than the divergence.
-        constexpr uint32_t kSortMask = (1u << SHB_SHA1) | (1u << SHB_SHA3) | (1u << SHB_BLAKE3) | (1u << SHB_K12);
+        // SHA-1 is light enough per byte that, on multi-kilobyte records, the scattered (TLB-unfriendly) order
+        // costs more than the divergence it removes (-24 % on 10-50 kB reads), so it is sorted below 4 KiB only.
+        const uint32_t kSortMask = (mean < 4096 ? (1u << SHB_SHA1) : 0u) | (1u << SHB_SHA3) | (1u << SHB_BLAKE3) | (1u << SHB_K12);
         const uint32_t *perm = nullptr;
         if (d_scratch && n >= 1024 && (want & kSortMask) && !(flags & SHB_FLAG_NO_LENGTH_SORT)) {
             void *pbuf = static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).perm_off;
@@ -133,11 +139,11 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         }
         for (int a = 0; a < SHB_N_ALGOS; a++) {
             if (!(want >> a & 1u)) continue;
-            if (long_mode && a == SHB_NTHASH) {
+            if (long_ok && a == SHB_NTHASH) {
                 CU(shb::launch_nthash_long(fused_upper, res, offs, n, slot_of[a], st));
-            } else if (long_mode && a == SHB_XXH3) {
+            } else if (long_ok && a == SHB_XXH3) {
                 CU(shb::launch_xxh3_long(fused_upper, res, offs, n, slot_of[a], st));
-            } else if (long_mode && a == SHB_K12 && d_scratch) {
+            } else if (long_mode && mean >= 8192 && a == SHB_K12 && d_scratch) {
                 ScratchLayout L(total_bytes, n);
                 CU(shb::launch_k12_long(fused_upper, res, offs, n, total_bytes, slot_of[a],
                                         static_cast<uint8_t *>(d_scratch) + L.b3_off, st));
@@ -312,7 +318,7 @@ int shb_submit(shb_batch *b, size_t n, const int *algos, int n_algos, unsigned f
     }
     const bool norm = flags & (SHB_FLAG_STRIP | SHB_FLAG_EMIT_SEQ);
     bool wants_b3_long = false;
-    for (int k = 0; k < n_algos; k++) wants_b3_long |= ((algos[k] == SHB_BLAKE3 || algos[k] == SHB_K12) && n && total / n >= 2048);
+    for (int k = 0; k < n_algos; k++) wants_b3_long |= ((algos[k] == SHB_BLAKE3 || algos[k] == SHB_K12) && n && total / n >= 4096);
     const bool direct_path = n && (total / n) * 128 * 17 / 16 + 2047 > 100 * 1024;   // mirrors run_pipeline's tile_mode
     if (norm || wants_b3_long || direct_path) {
         const size_t sneed = ScratchLayout(b->max_bytes, b->max_records).total;
