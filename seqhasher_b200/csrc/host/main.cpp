@@ -3,6 +3,7 @@
 // and decompression; everything inside processSequences' record loop (seqhasher.go:227-283) runs on the GPU
 // through shb_textproc.  Go's `flag` rules are reproduced: -x and --x alike, `-x=v` or `-x v`, parsing stops
 // at the first positional ("-" included) or after "--".
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,6 +14,12 @@
 #include "decompress.hpp"
 
 namespace {
+
+// SHB_TIMING=1: phase times on stderr (where does the wall time of one invocation go?)
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+const bool kTiming = getenv("SHB_TIMING") != nullptr;
+const double kT0 = now_s();
+void phase(const char *what) { if (kTiming) fprintf(stderr, "[timing] %-18s %.3f s\n", what, now_s() - kT0); }
 
 const char *kVersion = "1.2.0";   // seqhasher.go:38
 const char *kTypes[12] = {"sha1", "sha3", "md5", "xxhash", "xxh3", "cityhash", "murmur3", "nthash", "blake3", "k12",
@@ -142,8 +149,10 @@ int process_sequences(host::Source &in, FILE *out, const Config &cfg, std::strin
     }
     if (ids.size() > 12) { err = "at most 12 hash types per run are supported by the GPU formatter"; return 1; }
     size_t cap = (size_t)64 << 20;
+    phase("before create");
     shb_textproc *tp = shb_textproc_create(0, cap);
     if (!tp) { err = std::string("seqhash_b200: ") + shb_last_error(); return 1; }
+    phase("textproc created");
     uint8_t *buf = shb_textproc_input(tp);
     const unsigned flags = cfg.case_sensitive ? 0u : SHB_FLAG_UPPER;
     size_t fill = 0;
@@ -202,6 +211,7 @@ int process_sequences(host::Source &in, FILE *out, const Config &cfg, std::strin
         fill -= used;
     }
     fflush(out);
+    phase("records done");
     // no shb_textproc_destroy: unpinning the staging buffers costs about a second and the process is exiting
     return rc;
 }
