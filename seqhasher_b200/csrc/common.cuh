@@ -8,7 +8,7 @@
 //   SmemReader<UPPER>    — from a shared-memory tile that was staged by a TMA bulk copy; upper-
 //                          casing either fused in the load (one hash) or done in place beforehand
 // Both return words by funnel-shifting two aligned 32-bit loads, so no unaligned access is ever
-// issued; both may read (never use) up to 7 bytes past the record end, which the buffers pad.
+// issued; both may read (never use) up to 15 bytes past the record end, which the buffers pad (16 bytes).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
