@@ -42,11 +42,15 @@ __device__ __forceinline__ uint64_t xxh64_record(const R &r, uint32_t len)
     if (len >= 32) {
         uint64_t v1 = XP64_1 + XP64_2, v2 = XP64_2, v3 = 0, v4 = 0ULL - XP64_1;
         const uint32_t lim = len - 32;
+        auto in = r.stream(0);
         do {
-            v1 = xxh64_round(v1, r.u64(p));
-            v2 = xxh64_round(v2, r.u64(p + 8));
-            v3 = xxh64_round(v3, r.u64(p + 16));
-            v4 = xxh64_round(v4, r.u64(p + 24));
+            uint32_t a[4], b[4];
+            in.next(a);
+            in.next(b);
+            v1 = xxh64_round(v1, mk64(a[0], a[1]));
+            v2 = xxh64_round(v2, mk64(a[2], a[3]));
+            v3 = xxh64_round(v3, mk64(b[0], b[1]));
+            v4 = xxh64_round(v4, mk64(b[2], b[3]));
             p += 32;
         } while (p <= lim);
         h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
@@ -223,9 +227,12 @@ __device__ __forceinline__ void murmur3_record(const R &r, uint32_t len, uint64_
     const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
     uint64_t h1 = 0, h2 = 0;
     const uint32_t nblocks = len >> 4;
+    auto in = r.stream(0);
 #pragma unroll 4
     for (uint32_t i = 0; i < nblocks; i++) {
-        uint64_t k1 = r.u64(16 * i), k2 = r.u64(16 * i + 8);
+        uint32_t kw[4];
+        in.next(kw);
+        uint64_t k1 = mk64(kw[0], kw[1]), k2 = mk64(kw[2], kw[3]);
         k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
         h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ULL;
         k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
@@ -352,16 +359,25 @@ __device__ __forceinline__ CityPair city128_with_seed(const R &r, uint32_t s0, u
     v.second = rotr64(v.first, 42) * CK1 + r.u64x(s + 8);
     w.first = rotr64(y + z, 35) * CK1 + x;
     w.second = rotr64(x + r.u64x(s + 88), 53) * CK1;
+    auto in = r.stream(s);
     do {
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
-            x = rotr64(x + y + v.first + r.u64x(s + 8), 37) * CK1;
-            y = rotr64(y + v.second + r.u64x(s + 48), 42) * CK1;
+            uint64_t q[8];   // the 64-byte half-block, one 16-byte group at a time
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                uint32_t t4[4];
+                in.next(t4);
+                q[2 * g] = mk64(t4[0], t4[1]);
+                q[2 * g + 1] = mk64(t4[2], t4[3]);
+            }
+            x = rotr64(x + y + v.first + q[1], 37) * CK1;
+            y = rotr64(y + v.second + q[6], 42) * CK1;
             x ^= w.second;
-            y += v.first + r.u64x(s + 40);
+            y += v.first + q[5];
             z = rotr64(z + w.first, 33) * CK1;
-            v = city_weak32_at(r, s, v.second * CK1, x + w.first);
-            w = city_weak32_at(r, s + 32, z + w.second, y + r.u64x(s + 16));
+            v = city_weak32(q[0], q[1], q[2], q[3], v.second * CK1, x + w.first);
+            w = city_weak32(q[4], q[5], q[6], q[7], z + w.second, y + q[2]);
             uint64_t t = z; z = x; x = t;
             s += 64;
         }
@@ -474,10 +490,15 @@ __device__ __forceinline__ uint64_t rapidhash_record(const R &r, uint32_t len)
         uint32_t i = len, p = 0;
         if (i > 48) {
             uint64_t see1 = seed, see2 = seed;
+            auto in = r.stream(0);
             do {
-                seed = mulfold64(r.u64(p) ^ RAPID_S0, r.u64(p + 8) ^ seed);
-                see1 = mulfold64(r.u64(p + 16) ^ RAPID_S1, r.u64(p + 24) ^ see1);
-                see2 = mulfold64(r.u64(p + 32) ^ RAPID_S2, r.u64(p + 40) ^ see2);
+                uint32_t x[4], y[4], z[4];
+                in.next(x);
+                in.next(y);
+                in.next(z);
+                seed = mulfold64(mk64(x[0], x[1]) ^ RAPID_S0, mk64(x[2], x[3]) ^ seed);
+                see1 = mulfold64(mk64(y[0], y[1]) ^ RAPID_S1, mk64(y[2], y[3]) ^ see1);
+                see2 = mulfold64(mk64(z[0], z[1]) ^ RAPID_S2, mk64(z[2], z[3]) ^ see2);
                 p += 48;
                 i -= 48;
             } while (i >= 48);

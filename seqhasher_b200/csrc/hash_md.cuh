@@ -92,7 +92,9 @@ __device__ __forceinline__ uint32_t md_tail_word(const R &r, uint32_t off, uint3
 // out: 20 bytes, 4-byte aligned
 // (The branch-free md_tail_word form measured 8 % slower here when the reader also carries the whitespace
 // detector — the kernel runs at 20 warps/SM and the longer dependent chains of the tail stall it — so SHA-1
-// keeps the predicated padded_u32 tail; MD5 below is 7 % faster with md_tail_word.  A/B: tools/ab_quick.py.)
+// keeps the predicated padded_u32 tail; MD5 below is 7 % faster with md_tail_word.  A/B: tools/ab_quick.py.
+// Both keep 32-bit word loads on the direct path too: they are ALU-pipe-bound, and the select stages of the
+// 128-bit Stream reader cost 2-18 % there while the multiply-based hashes gain 1.5-2.9x, tools/ab_direct.py.)
 template <class R>
 __device__ __forceinline__ void sha1_record(const R &r, uint32_t len, uint8_t *out)
 {

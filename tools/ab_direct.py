@@ -1,0 +1,40 @@
+"""A/B of the direct (thread-per-record, global-memory) path on mid and long records.
+SHB_LIB selects the library; prints ms per pass and residue GB/s per (shape, algorithm, flags).
+Standalone ctypes loader so that older builds of the library can be compared."""
+import ctypes, os, sys, torch
+c = ctypes
+lib = os.environ.get("SHB_LIB") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "seqhasher_b200", "libseqhash_b200.so")
+L = ctypes.CDLL(lib)
+L.shb_init.argtypes = [c.c_int, c.c_int]
+L.shb_hash_device.argtypes = [c.c_int, c.c_void_p, c.c_void_p, c.c_size_t, c.c_size_t, c.POINTER(c.c_int), c.c_int, c.c_uint, c.POINTER(c.c_void_p), c.c_void_p, c.c_void_p, c.c_void_p]
+L.shb_synth_fill.argtypes = [c.c_int, c.c_void_p, c.c_size_t, c.c_uint64, c.c_uint, c.c_uint, c.c_void_p]
+L.shb_scratch_bytes.argtypes = [c.c_size_t, c.c_size_t]; L.shb_scratch_bytes.restype = c.c_size_t
+L.shb_init(1, 0)
+st = torch.cuda.current_stream().cuda_stream
+SIZES = {0: 20, 2: 16, 3: 8, 5: 16, 6: 16, 10: 8}
+NAMES = {0: "sha1", 2: "md5", 3: "xxhash", 5: "cityhash", 6: "murmur3", 10: "rapidhash"}
+SHAPES = {"readme": (500_000, 30, 3000), "mid1k": (1_000_000, 800, 1200), "c4": (20_000, 10_000, 50_000)}
+only = sys.argv[1].split(",") if len(sys.argv) > 1 else list(SHAPES)
+g = torch.Generator(device="cpu"); g.manual_seed(7)
+for shape in only:
+    n, lo, hi = SHAPES[shape]
+    lens = torch.randint(lo, hi + 1, (n,), generator=g, dtype=torch.int64)
+    offs = torch.zeros(n + 1, dtype=torch.int64); offs[1:] = torch.cumsum(lens, 0)
+    total = int(offs[-1])
+    d_offs = offs.cuda()
+    d_res = torch.empty(total + 16, dtype=torch.uint8, device="cuda")
+    L.shb_synth_fill(0, d_res.data_ptr(), total, 0xAB, 50, 0, st)
+    scr = torch.empty(L.shb_scratch_bytes(total, n), dtype=torch.uint8, device="cuda")
+    for algo in SIZES:
+        for flags in (0, 1):
+            out = torch.zeros(n * SIZES[algo], dtype=torch.uint8, device="cuda")
+            ids = (c.c_int * 1)(algo); ptrs = (c.c_void_p * 1)(out.data_ptr())
+            run = lambda: L.shb_hash_device(0, d_res.data_ptr(), d_offs.data_ptr(), n, total, ids, 1, flags, ptrs, None, scr.data_ptr(), st)
+            for _ in range(3): assert run() == 0
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10): run()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            chk = int(out.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFF   # digests must agree across builds
+            print(f"{os.path.basename(lib)} {shape} {NAMES[algo]} flags={flags} {ms:.4f} ms {total / ms / 1e6:.0f} GB/s chk={chk:012x}", flush=True)
