@@ -10,16 +10,17 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <algorithm>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
-namespace host {
+#include "pgzip.hpp"
+#include "readahead.hpp"
+#include "source.hpp"
 
-// A pull-style byte source: read() fills up to n bytes, returns 0 at end of input.
-struct Source {
-    virtual ~Source() {}
-    virtual size_t read(uint8_t *dst, size_t n) = 0;
-};
+namespace host {
 
 struct FileSource : Source {
     FILE *f;
@@ -215,14 +216,38 @@ struct XzSource : Inflater {
     }
 };
 
-// Sniff the magic bytes and wrap the file in the matching decompressor.
+// Worker threads for the parallel decompressors: SHB_DECOMP_THREADS, else the machine's hardware threads
+// (capped at 32); 1 selects the plain single-stream library paths.
+inline unsigned decomp_threads()
+{
+    if (const char *e = getenv("SHB_DECOMP_THREADS")) {
+        int v = atoi(e);
+        if (v >= 1) return (unsigned)std::min(v, 64);
+    }
+    unsigned hc = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hc ? hc : 1u, 32u));
+}
+
+// Sniff the magic bytes and wrap the file in the matching decompressor; compressed inputs are decoded on a
+// read-ahead thread so that they overlap the consumer.
 inline std::unique_ptr<Source> open_maybe_compressed(FILE *f, bool own)
 {
     auto fs = std::make_unique<FileSource>(f, own);
     uint8_t head[6];
     size_t k = fread(head, 1, sizeof head, f);
     fs->unread(head, k);
-    if (k >= 2 && head[0] == 0x1f && head[1] == 0x8b) return std::make_unique<GzipSource>(std::move(fs));
+    const unsigned threads = decomp_threads();
+    if (k >= 2 && head[0] == 0x1f && head[1] == 0x8b) {
+        if (threads >= 2) {
+            size_t piece = (size_t)2 << 20, min_piece = (size_t)256 << 10;
+            if (const char *e = getenv("SHB_PGZIP_PIECE_KB")) {   // tests: tiny pieces stress the chaining
+                long kb = atol(e);
+                if (kb >= 1) piece = min_piece = (size_t)kb << 10;
+            }
+            return std::make_unique<ReadAhead>(std::make_unique<ParallelGzipSource>(std::move(fs), threads, piece, min_piece));
+        }
+        return std::make_unique<GzipSource>(std::move(fs));
+    }
     if (k >= 3 && head[0] == 'B' && head[1] == 'Z' && head[2] == 'h') return std::make_unique<Bz2Source>(std::move(fs));
     if (k >= 6 && memcmp(head, "\xfd" "7zXZ\0", 6) == 0) return std::make_unique<XzSource>(std::move(fs));
     if (k >= 4 && head[0] == 0x28 && head[1] == 0xb5 && head[2] == 0x2f && head[3] == 0xfd) return std::make_unique<ZstdSource>(std::move(fs));

@@ -16,6 +16,7 @@ def pytest_sessionstart(session):
     """Fresh checkout: the built artefacts are git-ignored, so build them once (nvcc cross-compiles without a GPU)."""
     import subprocess
     need = [os.path.join(ROOT, "seqhasher_b200", "libseqhash_b200.so"), os.path.join(ROOT, "seqhasher_b200", "bin", "seqhasher-b200"),
+            os.path.join(ROOT, "seqhasher_b200", "bin", "shb-zcat"),
             os.path.join(ROOT, "oracle", "_build", "liboracle.so"), os.path.join(ROOT, "oracle", "_build", "cpu_bench")]
     if not all(os.path.exists(p) for p in need):
         subprocess.run(["make", "-C", os.path.join(ROOT, "seqhasher_b200", "csrc")], check=True, stdout=subprocess.DEVNULL)

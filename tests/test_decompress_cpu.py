@@ -1,0 +1,135 @@
+"""Decompression feeders of the compiled host (seqhasher_b200/csrc/host/decompress.hpp), no GPU needed.
+
+`shb-zcat` runs exactly the input stack the compiled CLI puts in front of the GPU record loop.  The parallel
+gzip reader (pgzip.hpp + inflate_markers.hpp) must reproduce zlib's output bit for bit on every kind of
+deflate stream, verify CRC-32/ISIZE like the reference's gzip reader, and fail on the same inputs
+(seqhasher_test.go:355-360 reads the .gz/.zst/.xz/.bz2 twins of test/test.fasta through this layer)."""
+import bz2
+import lzma
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ZCAT = os.path.join(ROOT, "seqhasher_b200", "bin", "shb-zcat")
+FIX = os.path.join(ROOT, "tests", "golden", "fixtures")
+
+
+def fasta(nbytes, seed, wrap=60):
+    r = np.random.default_rng(seed)
+    alpha = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    out, tot, i = [], 0, 0
+    while tot < nbytes:
+        L = int(r.integers(30, 3000))
+        seq = alpha[r.integers(0, 4 if i % 7 else 9, size=L)].tobytes()
+        rec = b">s%d\n" % i + b"\n".join(seq[j:j + wrap] for j in range(0, L, wrap)) + b"\n"
+        out.append(rec)
+        tot += len(rec)
+        i += 1
+    return b"".join(out)
+
+
+def gz(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, flags=0, extra=b"", name=b"", comment=b""):
+    c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+    body = c.compress(data) + c.flush()
+    flg = (4 if extra else 0) | (8 if name else 0) | (16 if comment else 0) | flags
+    hdr = b"\x1f\x8b\x08" + bytes([flg]) + b"\0\0\0\0\0\x03"
+    if extra:
+        hdr += struct.pack("<H", len(extra)) + extra
+    if name:
+        hdr += name + b"\0"
+    if comment:
+        hdr += comment + b"\0"
+    if flg & 2:
+        hdr += struct.pack("<H", zlib.crc32(hdr) & 0xFFFF)
+    return hdr + body + struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data) & 0xFFFFFFFF)
+
+
+def zcat(blob, threads=4, piece_kb=None):
+    env = dict(os.environ, SHB_DECOMP_THREADS=str(threads))
+    if piece_kb:
+        env["SHB_PGZIP_PIECE_KB"] = str(piece_kb)
+    p = subprocess.run([ZCAT, "-"], input=blob, capture_output=True, env=env, timeout=300)
+    return p.returncode, p.stdout, p.stderr.decode()
+
+
+DATA = fasta(6_000_000, seed=1)
+CASES = {
+    "level1": lambda: (gz(DATA, 1), DATA),
+    "level6": lambda: (gz(DATA, 6), DATA),
+    "level9": lambda: (gz(DATA, 9), DATA),
+    "fixed_huffman": lambda: (gz(DATA[:2_000_000], 6, zlib.Z_FIXED), DATA[:2_000_000]),
+    "huffman_only": lambda: (gz(DATA[:2_000_000], 6, zlib.Z_HUFFMAN_ONLY), DATA[:2_000_000]),
+    "rle": lambda: (gz(DATA[:2_000_000], 6, zlib.Z_RLE), DATA[:2_000_000]),
+    "stored": lambda: (gz(DATA[:1_500_000], 0), DATA[:1_500_000]),
+    "incompressible": lambda: (lambda r: (gz(r, 6), r))(np.random.default_rng(3).bytes(1_500_000)),
+    "header_fields": lambda: (gz(DATA[:900_000], 6, flags=2, extra=b"AB\x02\x00xy", name=b"f.fa", comment=b"c"), DATA[:900_000]),
+    "multi_member": lambda: (b"".join(gz(DATA[i:i + 300_001], 6, name=b"x") for i in range(0, 3_000_000, 300_001)),
+                             DATA[:3_000_010]),
+    "bgzf_like": lambda: (b"".join(gz(DATA[i:i + 65280], 6, extra=b"BC\x02\x00\x00\x00") for i in range(0, 2_000_000, 65280)) + gz(b""),
+                          DATA[:(2_000_000 + 65279) // 65280 * 65280]),
+    "empty_member": lambda: (gz(b""), b""),
+    "tiny": lambda: (gz(b">a\nACGT\n"), b">a\nACGT\n"),
+    "members_with_empties": lambda: (gz(b"") + gz(b">a\nAC\n") + gz(b"") + gz(b"GT\n"), b">a\nAC\nGT\n"),
+    "mixed": lambda: (lambda m: (gz(m, 6), m))(DATA[:1_000_000] + np.random.default_rng(4).bytes(700_000) + DATA[1_000_000:2_500_000]
+                                               + b"A" * 2_000_000 + DATA[:1000]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("threads,piece_kb", [(1, None), (2, None), (4, 64), (8, 16)])
+def test_gzip_streams_match_zlib(name, threads, piece_kb):
+    blob, want = CASES[name]()
+    rc, out, err = zcat(blob, threads, piece_kb)
+    assert rc == 0, err
+    assert out == want
+
+
+def test_gzip_budget_path_on_a_1000_to_1_stream():
+    # one deflate piece inflating 1000:1 is handed out over several batches (PIECE_BUDGET)
+    want = b">polyA\n" + b"A" * 120_000_000 + b"\n"
+    rc, out, err = zcat(gz(want, 6), 4)
+    assert rc == 0, err
+    assert out == want
+
+
+def test_gzip_errors_like_the_reference_reader():
+    blob = gz(DATA[:2_000_000], 6)
+    rc, out, err = zcat(blob[:-50_000], 4, 64)
+    assert rc == 1 and "unexpected EOF" in err
+    assert DATA.startswith(out) and len(out) > 1_000_000   # what was complete is still delivered first
+    bad = bytearray(blob)
+    bad[-6] ^= 0x55
+    rc, _, err = zcat(bytes(bad), 4, 64)
+    assert rc == 1 and "invalid checksum" in err
+    rc, _, err = zcat(blob + b"\0" * 512, 4, 64)
+    assert rc == 1 and "invalid header" in err
+    bad = bytearray(blob)
+    bad[300_000] ^= 0xFF
+    rc, _, err = zcat(bytes(bad), 4, 64)
+    assert rc == 1 and ("invalid" in err or "EOF" in err)
+
+
+@pytest.mark.parametrize("ext", ["", ".gz", ".zst", ".xz", ".bz2"])
+def test_reference_fixture_twins_decompress_identically(ext):
+    plain = open(os.path.join(FIX, "test.fasta"), "rb").read()
+    path = os.path.join(FIX, "test.fasta" + ext)
+    if not os.path.exists(path):
+        pytest.skip("fixture twin not present")
+    p = subprocess.run([ZCAT, path], capture_output=True, timeout=60)
+    assert p.returncode == 0, p.stderr.decode()
+    assert p.stdout == plain
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_bzip2_and_xz_streams(threads):
+    data = DATA[:3_000_000]
+    for blob in (bz2.compress(data, 1), bz2.compress(data[:1_000_000], 9) + bz2.compress(data[1_000_000:], 5),
+                 lzma.compress(data, preset=1), lzma.compress(data[:1_500_000], preset=0) + lzma.compress(data[1_500_000:], preset=0)):
+        rc, out, err = zcat(blob, threads)
+        assert rc == 0, err
+        assert out == data
