@@ -16,6 +16,7 @@
 #include <thread>
 #include <vector>
 
+#include "pbzip2.hpp"
 #include "pgzip.hpp"
 #include "readahead.hpp"
 #include "source.hpp"
@@ -72,7 +73,10 @@ struct GzipSource : Inflater {
         size_t produced = 0;
         while (produced < n && !done) {
             refill();
-            if (in_pos == in_len && src_eof) { done = true; break; }
+            if (in_pos == in_len && src_eof) {   // input ended inside a member
+                if (produced) break;
+                throw std::runtime_error("unexpected EOF");
+            }
             z.next_in = in.data() + in_pos;
             z.avail_in = (uInt)(in_len - in_pos);
             z.next_out = dst + produced;
@@ -95,6 +99,7 @@ struct GzipSource : Inflater {
 struct ZstdSource : Inflater {
     struct Buf { void *p; size_t size, pos; };
     void *lib = nullptr, *ds = nullptr;
+    bool mid_frame = false;
     void *(*create)() = nullptr;
     size_t (*freeds)(void *) = nullptr;
     size_t (*decompress)(void *, Buf *, Buf *) = nullptr;
@@ -116,11 +121,16 @@ struct ZstdSource : Inflater {
         Buf out{dst, n, 0};
         while (out.pos < n && !done) {
             refill();
-            if (in_pos == in_len && src_eof) { done = true; break; }
+            if (in_pos == in_len && src_eof) {
+                if (!mid_frame) { done = true; break; }
+                if (out.pos) break;
+                throw std::runtime_error("unexpected EOF");   // input ended inside a frame
+            }
             Buf ib{in.data(), in_len, in_pos};
             size_t rc = decompress(ds, &out, &ib);
             in_pos = ib.pos;
             if (is_error(rc)) throw std::runtime_error("zstd: invalid compressed data");
+            mid_frame = rc != 0;
         }
         return out.pos;
     }
@@ -153,7 +163,10 @@ struct Bz2Source : Inflater {
         size_t produced = 0;
         while (produced < n && !done) {
             refill();
-            if (in_pos == in_len && src_eof) { done = true; break; }
+            if (in_pos == in_len && src_eof) {   // input ended inside a stream
+                if (produced) break;
+                throw std::runtime_error("unexpected EOF");
+            }
             z.next_in = (char *)in.data() + in_pos;
             z.avail_in = (unsigned)(in_len - in_pos);
             z.next_out = (char *)dst + produced;
@@ -183,10 +196,23 @@ struct XzSource : Inflater {
         int reserved_enum1, reserved_enum2;
     } z;
     void *lib = nullptr;
+    bool pending_eof = false;
     int (*decoder)(lzma_stream *, uint64_t, uint32_t) = nullptr;
     int (*code)(lzma_stream *, int) = nullptr;
     void (*end)(lzma_stream *) = nullptr;
-    explicit XzSource(std::unique_ptr<Source> s) : Inflater(std::move(s))
+    // lzma_mt of liblzma >= 5.4 (the threaded decoder splits multi-block files, i.e. what `xz -T` writes;
+    // single-block files run on one thread inside the same call)
+    struct lzma_mt {
+        uint32_t flags, threads;
+        uint64_t block_size;
+        uint32_t timeout, preset;
+        const void *filters;
+        int check, reserved_enum1, reserved_enum2, reserved_enum3;
+        uint32_t reserved_int1, reserved_int2, reserved_int3, reserved_int4;
+        uint64_t memlimit_threading, memlimit_stop, reserved_int7, reserved_int8;
+        void *reserved_ptr1, *reserved_ptr2, *reserved_ptr3, *reserved_ptr4;
+    };
+    explicit XzSource(std::unique_ptr<Source> s, unsigned threads = 1) : Inflater(std::move(s))
     {
         lib = dlopen("liblzma.so.5", RTLD_NOW | RTLD_LOCAL);
         if (!lib) throw std::runtime_error("xz: liblzma.so.5 not available");
@@ -194,12 +220,25 @@ struct XzSource : Inflater {
         code = (int (*)(lzma_stream *, int))dlsym(lib, "lzma_code");
         end = (void (*)(lzma_stream *))dlsym(lib, "lzma_end");
         memset(&z, 0, sizeof z);
-        if (!decoder || !code || !end || decoder(&z, UINT64_MAX, 0x08 /* LZMA_CONCATENATED */) != 0)
-            throw std::runtime_error("xz: init failed");
+        if (!decoder || !code || !end) throw std::runtime_error("xz: symbols missing");
+        auto decoder_mt = (int (*)(lzma_stream *, const lzma_mt *))dlsym(lib, "lzma_stream_decoder_mt");
+        bool ok = false;
+        if (threads >= 2 && decoder_mt) {
+            lzma_mt mt;
+            memset(&mt, 0, sizeof mt);
+            mt.flags = 0x08;   // LZMA_CONCATENATED
+            mt.threads = threads;
+            mt.memlimit_threading = (uint64_t)4 << 30;
+            mt.memlimit_stop = UINT64_MAX;
+            ok = decoder_mt(&z, &mt) == 0;
+            if (!ok) memset(&z, 0, sizeof z);
+        }
+        if (!ok && decoder(&z, UINT64_MAX, 0x08 /* LZMA_CONCATENATED */) != 0) throw std::runtime_error("xz: init failed");
     }
     ~XzSource() override { if (end) end(&z); }
     size_t read(uint8_t *dst, size_t n) override
     {
+        if (pending_eof) throw std::runtime_error("unexpected EOF");
         z.next_out = dst;
         z.avail_out = n;
         while (z.avail_out && !done) {
@@ -210,7 +249,10 @@ struct XzSource : Inflater {
             in_pos = in_len - z.avail_in;
             if (rc == 1 /* LZMA_STREAM_END */) done = true;
             else if (rc != 0 && rc != 10 /* LZMA_BUF_ERROR */) throw std::runtime_error("xz: invalid compressed data");
-            else if (rc == 10 && in_pos == in_len && src_eof) done = true;
+            else if (rc == 10 && in_pos == in_len && src_eof) {   // input ended inside a stream
+                if (z.avail_out != n) { pending_eof = true; break; }   // hand out what was decoded first
+                throw std::runtime_error("unexpected EOF");
+            }
         }
         return n - z.avail_out;
     }
@@ -248,9 +290,18 @@ inline std::unique_ptr<Source> open_maybe_compressed(FILE *f, bool own)
         }
         return std::make_unique<GzipSource>(std::move(fs));
     }
-    if (k >= 3 && head[0] == 'B' && head[1] == 'Z' && head[2] == 'h') return std::make_unique<Bz2Source>(std::move(fs));
-    if (k >= 6 && memcmp(head, "\xfd" "7zXZ\0", 6) == 0) return std::make_unique<XzSource>(std::move(fs));
-    if (k >= 4 && head[0] == 0x28 && head[1] == 0xb5 && head[2] == 0x2f && head[3] == 0xfd) return std::make_unique<ZstdSource>(std::move(fs));
+    if (k >= 3 && head[0] == 'B' && head[1] == 'Z' && head[2] == 'h') {
+        if (threads >= 2) return std::make_unique<ReadAhead>(std::make_unique<ParallelBz2Source>(std::move(fs), threads));
+        return std::make_unique<Bz2Source>(std::move(fs));
+    }
+    if (k >= 6 && memcmp(head, "\xfd" "7zXZ\0", 6) == 0) {
+        if (threads >= 2) return std::make_unique<ReadAhead>(std::make_unique<XzSource>(std::move(fs), threads));
+        return std::make_unique<XzSource>(std::move(fs));
+    }
+    if (k >= 4 && head[0] == 0x28 && head[1] == 0xb5 && head[2] == 0x2f && head[3] == 0xfd) {
+        if (threads >= 2) return std::make_unique<ReadAhead>(std::make_unique<ZstdSource>(std::move(fs)));
+        return std::make_unique<ZstdSource>(std::move(fs));
+    }
     return fs;
 }
 

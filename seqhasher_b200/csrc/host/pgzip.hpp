@@ -154,7 +154,10 @@ struct ParallelGzipSource : Source {
         size_t produced = 0;
         while (produced < n) {
             if (out_pos == out_len) {
-                if (!pending_error.empty()) throw std::runtime_error(pending_error);
+                if (!pending_error.empty()) {
+                    if (produced) break;   // bytes decoded before the failure go out first
+                    throw std::runtime_error(pending_error);
+                }
                 if (finished) break;
                 // a whole batch is resolved straight into the caller's buffer when it fits (short read)
                 size_t direct = next_batch(dst + produced, n - produced);

@@ -133,3 +133,52 @@ def test_bzip2_and_xz_streams(threads):
         rc, out, err = zcat(blob, threads)
         assert rc == 0, err
         assert out == data
+
+
+def test_bzip2_edge_cases_parallel():
+    poly = b">polyA\n" + b"A" * 30_000_000 + b"\n"          # run-length expansion far beyond the block size
+    small_blocks = b"".join(bz2.compress(DATA[i:i + 150_000], 1) for i in range(0, 1_500_000, 150_000))   # 10 streams
+    for blob, want in ((bz2.compress(b""), b""), (bz2.compress(b">a\nACGT\n"), b">a\nACGT\n"), (bz2.compress(poly, 9), poly),
+                       (small_blocks, DATA[:1_500_000]), (bz2.compress(b"") + bz2.compress(b"xyz"), b"xyz")):
+        rc, out, err = zcat(blob, 4)
+        assert rc == 0, err
+        assert out == want
+    blob = bz2.compress(DATA[:3_000_000], 5)
+    rc, out, err = zcat(blob[:-40_000], 4)
+    assert rc == 1 and "EOF" in err and DATA.startswith(out) and len(out) > 1_000_000
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0x10
+    rc, out, err = zcat(bytes(bad), 4)
+    assert rc == 1 and "bzip2" in err and DATA.startswith(out)
+    bad = bytearray(blob)
+    bad[-2] ^= 0x01                                           # stream (combined) CRC
+    rc, out, err = zcat(bytes(bad), 4)
+    assert rc == 1 and "checksum" in err
+
+
+def test_xz_multiblock_threaded():
+    import shutil
+    if not shutil.which("xz"):
+        pytest.skip("xz CLI not installed")
+    data = DATA[:5_000_000]
+    blob = subprocess.run(["xz", "-c", "-T2", "-1", "--block-size=512KiB"], input=data, capture_output=True, check=True).stdout
+    for threads in (1, 4):
+        rc, out, err = zcat(blob, threads)
+        assert rc == 0, err
+        assert out == data
+    rc, out, err = zcat(blob[:-30_000], 4)
+    assert rc == 1
+
+
+def test_truncated_inputs_fail_on_the_single_thread_paths_too():
+    import shutil
+    data = DATA[:1_000_000]
+    blobs = [gz(data, 6), bz2.compress(data, 3), lzma.compress(data, preset=0)]
+    if shutil.which("zstd"):
+        blobs.append(subprocess.run(["zstd", "-c", "-3"], input=data, capture_output=True, check=True).stdout)
+    for blob in blobs:
+        rc, out, err = zcat(blob, 1)
+        assert rc == 0 and out == data, err
+        rc, out, err = zcat(blob[:len(blob) * 2 // 3], 1)
+        assert rc == 1 and "EOF" in err, (blob[:4], err)
+        assert data.startswith(out)
