@@ -28,7 +28,7 @@ struct ReadAhead : Source {
     std::exception_ptr err;
     std::thread th;
 
-    explicit ReadAhead(std::unique_ptr<Source> s, size_t buf_bytes = (size_t)64 << 20) : src(std::move(s)), cap(buf_bytes)
+    explicit ReadAhead(std::unique_ptr<Source> s, size_t buf_bytes = (size_t)192 << 20) : src(std::move(s)), cap(buf_bytes)
     {
         for (auto &b : bufs) b.d.reset(new uint8_t[buf_bytes]);
         th = std::thread([this] { feeder(); });
