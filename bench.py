@@ -48,11 +48,12 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.samples, self.proc = index, [], None
+        self.t_load = None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -62,18 +63,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.monotonic(), line.strip()))
+
+    def wait_ready(self, timeout=5.0):
+        """nvidia-smi needs 0.1-1 s to start (longer on an 8-GPU box): wait for its first line."""
+        t0 = time.monotonic()
+        while self.proc and not self.samples and time.monotonic() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark_load(self):
+        self.t_load = time.monotonic()
+
+    def under_load(self):
+        return [s for t, s in self.samples if self.t_load is not None and t >= self.t_load]
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.15)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in self.under_load():
             parts = [x.strip() for x in s.split(",")]
             if len(parts) < 6:
                 continue
@@ -123,10 +135,31 @@ def run_reference(args):
                              "single_thread_value": r1["seqs_per_s"]},
             "e2e": {"value": val, "unit": "seqs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries underneath (NCCL prints its version banner with
+    printf) write to fd 1 too, so fd 1 is pointed at stderr for the rest of the run and the JSON line goes to
+    a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -183,21 +216,31 @@ def main():
         out = torch.empty(n * B.DIGEST_SIZES[B.algo_id(algo)], dtype=torch.uint8, device=dev)
         run = lambda: B.hash_device(d_res.data_ptr(), d_offs.data_ptr(), n, total, [algo], flags, [out.data_ptr()],
                                     d_scratch=d_scratch.data_ptr(), stream=st, device=local)
-        for _ in range(args.warmup):
-            run()
-        barrier()
-        l0 = B.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as cs:
+            cs.wait_ready()
+            for _ in range(args.warmup):
+                run()
+            barrier()
+            l0 = B.launch_count()
+            cs.mark_load()
             e0.record()
             for _ in range(args.steps):
                 run()
             e1.record()
             torch.cuda.synchronize()
-        launches = B.launch_count() - l0
+            launches = B.launch_count() - l0
+            # The timed region lasts a few tens of ms, nvidia-smi samples every 25 ms: keep the SAME launches
+            # going (outside the event bracket) until at least 4 samples were taken under this load.
+            t_tail = time.monotonic()
+            while len(cs.under_load()) < 4 and time.monotonic() - t_tail < 1.0:
+                run()
+                torch.cuda.synchronize()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        return ms, launches, cs.summary(), out
+        summ = cs.summary()
+        summ["window"] = "timed region + the same launches continued until 4 samples (25 ms period) were taken"
+        return ms, launches, summ, out
 
     ms_sha1, launches, clocks, out_sha1 = time_kernel("sha1")
     ms_xxh3, _, clocks_x, _ = time_kernel("xxh3")
@@ -339,7 +382,7 @@ def main():
                 "xxh3": {"value": n * world / (ms_xxh3 * 1e-3), "unit": "seqs/s", "ms_per_step": ms_xxh3,
                          "gbps": n * world * L / (ms_xxh3 * 1e-3) / 1e9, "roofline": roof_xxh3, "clocks": clocks_x},
                 "cpu_baseline": cpu, "e2e": e2e, "e2e_text": e2e_text, "gpu_launches": launches, "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
