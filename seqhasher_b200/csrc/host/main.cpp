@@ -159,9 +159,18 @@ int process_sequences(host::Source &in, FILE *out, const Config &cfg, std::strin
     int format = 0;
     bool eof = false;
     int rc = 0;
+    std::string read_err;
     while (true) {
         while (!eof && fill < cap) {
-            size_t got = in.read(buf + fill, cap - fill);
+            size_t got = 0;
+            try {
+                got = in.read(buf + fill, cap - fill);
+            } catch (const std::exception &e) {
+                // A damaged or truncated input: the records that are complete in what was decoded before the
+                // failure are still written (as a non-final chunk), then the error is reported — the reference's
+                // reader also fails on the record it cannot finish, not on the ones before it.
+                read_err = std::string("Error reading record: ") + e.what();
+            }
             if (got == 0) eof = true;
             fill += got;
         }
@@ -183,7 +192,7 @@ int process_sequences(host::Source &in, FILE *out, const Config &cfg, std::strin
             while (fill > 0 && is_blank(buf[fill - 1])) fill--;   // trailing blank lines are not records
             if (fill == 0) break;
         }
-        if (shb_textproc_run(tp, fill, format, eof ? 1 : 0, ids.empty() ? nullptr : ids.data(), (int)ids.size(), flags,
+        if (shb_textproc_run(tp, fill, format, (eof && read_err.empty()) ? 1 : 0, ids.empty() ? nullptr : ids.data(), (int)ids.size(), flags,
                              cfg.headers_only ? 1 : 0, no_file_name ? nullptr : label.c_str()) < 0) {
             err = std::string("Error reading record: ") + shb_last_error();
             rc = 1;
@@ -210,6 +219,7 @@ int process_sequences(host::Source &in, FILE *out, const Config &cfg, std::strin
         memmove(buf, buf + used, fill - used);
         fill -= used;
     }
+    if (rc == 0 && !read_err.empty()) { err = read_err; rc = 1; }
     fflush(out);
     phase("records done");
     // no shb_textproc_destroy: unpinning the staging buffers costs about a second and the process is exiting

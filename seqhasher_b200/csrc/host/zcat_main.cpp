@@ -25,7 +25,7 @@ int main(int argc, char **argv)
     try {
         auto t0 = std::chrono::steady_clock::now();
         auto src = host::open_maybe_compressed(f, f != stdin);
-        std::vector<uint8_t> buf((size_t)8 << 20);
+        std::vector<uint8_t> buf((size_t)32 << 20);
         size_t total = 0;
         for (;;) {
             size_t got = src->read(buf.data(), buf.size());

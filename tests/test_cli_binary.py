@@ -71,3 +71,83 @@ def test_binary_long_sequences_output_file_and_empty_record(tmp_path):
     assert out.splitlines()[-1] == "problematic_sequences.fasta;;;seq_empty" and err.count("Empty DNA sequence") == 2
     rc, _, err = run(["-"], stdin=b"not a sequence file\n")
     assert rc == 1 and err.strip() == "Failed to create reader: fastx: invalid FASTA/Q format"
+
+
+def _records(n, seed, lo=30, hi=3000, wrap=0):
+    import numpy as np
+    r = np.random.default_rng(seed)
+    lens = r.integers(lo, hi + 1, size=n)
+    seq = r.choice(np.frombuffer(b"ACGTacgt", dtype=np.uint8), size=int(lens.sum())).tobytes()
+    recs, pos = [], 0
+    for i, L in enumerate(lens):
+        recs.append((b"r%d" % i, seq[pos:pos + L]))
+        pos += L
+    text = b"".join(b">" + nm + b" d\n" + (b"\n".join(s[j:j + wrap] for j in range(0, len(s), wrap)) if wrap else s) + b"\n"
+                    for nm, s in recs)
+    return recs, text
+
+
+def _expected_headers(recs, label=None):
+    import hashlib
+    pre = (label + b";") if label else b""
+    return b"".join(pre + hashlib.sha1(s.upper()).hexdigest().encode() + b";" + nm + b" d\n" for nm, s in recs)
+
+
+@pytest.mark.gpu
+def test_binary_many_chunks_plain_stdin_and_gzip(tmp_path):
+    """> 64 MB of text = several chunks through the record loop: output order and carried partial records; file
+    (parallel pread) vs stdin vs gzip input (parallel feeder on a read-ahead thread) must all give the same bytes."""
+    import gzip
+    recs, text = _records(150_000, seed=21, wrap=70)          # ~230 MB, 4 chunks
+    want = _expected_headers(recs)
+    p = tmp_path / "many.fa"
+    p.write_bytes(text)
+    rc, out, err = run(["--headersonly", "--nofilename", str(p), "-"])
+    assert rc == 0, err
+    assert out.encode() == want
+    rc, out, err = run(["--headersonly", "--nofilename", "-"], stdin=text)
+    assert rc == 0 and out.encode() == want
+    g = tmp_path / "many.fa.gz"
+    g.write_bytes(gzip.compress(text, 1))
+    rc, out, err = run(["--headersonly", "--nofilename", str(g), "-"])
+    assert rc == 0 and out.encode() == want
+    # full-record output: sequences unwrapped and upper-cased
+    rc, out, err = run(["--nofilename", str(p), "-"])
+    lines = out.encode().split(b"\n")
+    assert rc == 0 and len(lines) == 2 * len(recs) + 1
+    assert lines[1] == recs[0][1].upper() and lines[-2] == recs[-1][1].upper()
+    assert lines[2 * 77_777] == b">" + _expected_headers([recs[77_777]])[:-1]
+
+
+@pytest.mark.gpu
+def test_binary_grows_its_buffer_for_a_giant_record(tmp_path):
+    """A record larger than the 64 MB chunk buffer (chromosome-sized FASTA entries) in the middle of a multi-chunk file."""
+    import hashlib
+    import numpy as np
+    recs_a, text_a = _records(60_000, seed=5)                  # ~90 MB: the giant record starts in chunk 2
+    big = np.random.default_rng(9).choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=150_000_000).tobytes()
+    recs_b, text_b = _records(2_000, seed=6)
+    recs_b = [(b"t" + nm, s) for nm, s in recs_b]
+    text_b = text_b.replace(b">r", b">tr")
+    text = text_a + b">giant d\n" + big + b"\n" + text_b
+    p = tmp_path / "giant.fa"
+    p.write_bytes(text)
+    rc, out, err = run(["--headersonly", "--nofilename", "--casesensitive", str(p), "-"])
+    assert rc == 0, err
+    import hashlib as H
+    want = b"".join(H.sha1(s).hexdigest().encode() + b";" + nm + b" d\n" for nm, s in recs_a + [(b"giant", big)] + recs_b)
+    assert out.encode() == want
+
+
+@pytest.mark.gpu
+def test_binary_truncated_gzip_writes_complete_records_then_fails(tmp_path):
+    import gzip
+    recs, text = _records(40_000, seed=8)
+    blob = gzip.compress(text, 1)
+    g = tmp_path / "cut.fa.gz"
+    g.write_bytes(blob[:len(blob) * 3 // 4])
+    rc, out, err = run(["--headersonly", "--nofilename", str(g), "-"])
+    assert rc == 1 and "unexpected EOF" in err
+    got = out.encode()
+    want = _expected_headers(recs)
+    assert len(got) > len(want) // 2 and want.startswith(got)
