@@ -15,6 +15,7 @@ SIZES = {0: 20, 2: 16, 3: 8, 5: 16, 6: 16, 10: 8}
 NAMES = {0: "sha1", 2: "md5", 3: "xxhash", 5: "cityhash", 6: "murmur3", 10: "rapidhash"}
 SHAPES = {"readme": (500_000, 30, 3000), "mid1k": (1_000_000, 800, 1200), "c4": (20_000, 10_000, 50_000)}
 only = sys.argv[1].split(",") if len(sys.argv) > 1 else list(SHAPES)
+algo_filter = sys.argv[2].split(",") if len(sys.argv) > 2 else list(NAMES.values())
 g = torch.Generator(device="cpu"); g.manual_seed(7)
 for shape in only:
     n, lo, hi = SHAPES[shape]
@@ -26,6 +27,8 @@ for shape in only:
     L.shb_synth_fill(0, d_res.data_ptr(), total, 0xAB, 50, 0, st)
     scr = torch.empty(L.shb_scratch_bytes(total, n), dtype=torch.uint8, device="cuda")
     for algo in SIZES:
+        if NAMES[algo] not in algo_filter:
+            continue
         for flags in (0, 1):
             out = torch.zeros(n * SIZES[algo], dtype=torch.uint8, device="cuda")
             ids = (c.c_int * 1)(algo); ptrs = (c.c_void_p * 1)(out.data_ptr())
