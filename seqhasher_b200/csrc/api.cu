@@ -1,6 +1,7 @@
 // api.cu — the C ABI of include/seqhash_b200.h: device selection, batch objects (pinned staging,
 // device buffers, one stream each), the submit/wait pipeline and the device-resident entry point.
 // There is no CPU fallback anywhere in this file: without a usable sm_100 device every call fails.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -125,16 +126,33 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         // BLAKE3 and K12 only pay off for multi-kilobyte records (below, the length-sorted direct kernels win).
         const bool long_ok = n && !(flags & (SHB_FLAG_FORCE_DIRECT | SHB_FLAG_NO_LONG_PATH));
         const bool long_mode = long_ok && mean >= 4096;
-        // The INT-bound thread-per-record kernels walk the records in descending length order so a warp's 32
-        // records finish together (sha1 +49 %, sha3 +85 %, blake3 +52 %, k12 +86 % on 30-3000-byte records);
-        // the memory-bound hashes keep input order: for them the lost locality costs more than the divergence.
-        // SHA-1 is light enough per byte that, on multi-kilobyte records, the scattered (TLB-unfriendly) order
-        // costs more than the divergence it removes (-24 % on 10-50 kB reads), so it is sorted below 4 KiB only.
-        const uint32_t kSortMask = (mean < 4096 ? (1u << SHB_SHA1) : 0u) | (1u << SHB_SHA3) | (1u << SHB_BLAKE3) | (1u << SHB_K12);
+        // Thread-per-record kernels can walk the records in descending length order (counting sort of the indices by
+        // 64-byte blocks) so that a warp's 32 records finish together.  Whether that pays is decided on the device
+        // (one order per batch: the lowest threshold among the requested algorithms; below it the permutation is the
+        // identity) from the sort's own histogram: w = E[longest of 32 records] / E[record] is what input order wastes, the
+        // scattered reads of sorted order cost more the longer the records and the lighter the hash per byte
+        // (tools/ab_direct.py, sorted vs input order on one B200):
+        //   sha3 / k12 / blake3 (direct)   sorted whenever lengths differ at all: x1.15 (w 1.19) ... x2.2 (w 1.9)
+        //   sha1                           same below 16 kB mean (x1.17 ... x2.0; 10-50 kB reads: x0.9-1.0)
+        //   md5                            w >= 1.15 and mean < 16 kB (x1.2 ... x1.9; 10-50 kB reads: x0.6-0.7)
+        //   xxhash / cityhash / murmur3 / rapidhash(32)   w >= 1.4 and mean < 2.5 kB (x1.1 ... x1.6 on 30-3000 bp;
+        //                                  x0.6-0.8 at 2-8 kB, x0.3-0.5 at 10-50 kB)
+        const uint32_t kHeavy = (1u << SHB_SHA3) | (1u << SHB_BLAKE3) | (1u << SHB_K12);
+        const uint32_t kStream = (1u << SHB_XXHASH) | (1u << SHB_CITYHASH) | (1u << SHB_MURMUR3) | (1u << SHB_RAPIDHASH) |
+                                 (1u << SHB_RAPIDHASH32);
+        const uint32_t kSortMask = kHeavy | (mean < 16384 ? (1u << SHB_SHA1) | (1u << SHB_MD5) : 0u) | (mean < 2560 ? kStream : 0u);
+        auto min_waste_q8 = [&](int a) -> uint32_t {   // x256
+            if (kStream >> a & 1u) return 358u;        // 1.40
+            if (a == SHB_MD5) return 294u;             // 1.15
+            return 269u;                               // 1.05
+        };
         const uint32_t *perm = nullptr;
         if (d_scratch && n >= 1024 && (want & kSortMask) && !(flags & SHB_FLAG_NO_LENGTH_SORT)) {
+            uint32_t lowest = 0xffffffffu;
+            for (int a = 0; a < SHB_N_ALGOS; a++)
+                if ((want & kSortMask) >> a & 1u) lowest = std::min(lowest, min_waste_q8(a));
             void *pbuf = static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).perm_off;
-            CU(shb::launch_length_sort(offs, n, pbuf, st));
+            CU(shb::launch_length_sort(offs, n, pbuf, lowest, st));
             perm = static_cast<const uint32_t *>(pbuf);
         }
         for (int a = 0; a < SHB_N_ALGOS; a++) {

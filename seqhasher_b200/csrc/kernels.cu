@@ -16,6 +16,8 @@ std::atomic<unsigned long long> g_launches{0};
 
 // perm (may be null): records in descending length order, so the 32 records of a warp need about the same
 // number of blocks; digests are still written at the record's own index (input order).
+constexpr uint32_t LEN_BUCKETS = 4096;   // 64-byte granularity up to 256 KiB, longer records share the first bucket
+// layout of launch_length_sort's buffer: perm[n] | pad to 256 | hist[LEN_BUCKETS] | waste_q8
 template <int ALGO, bool UPPER>
 __global__ void __launch_bounds__(128) hash_direct_kernel(const uint8_t *__restrict__ res,
                                                           const int64_t *__restrict__ offs, size_t n,
@@ -74,8 +76,6 @@ cudaError_t launch_hash_direct(int algo, bool upper, const uint8_t *res, const i
 // Length binning for the thread-per-record kernels: a counting sort of the record indices by
 // ceil(len / 64) (descending), so that a warp's 32 records finish together.  Thread-per-record over
 // 30-3000-byte records otherwise runs every warp for its longest record (about half the lanes idle).
-constexpr uint32_t LEN_BUCKETS = 4096;   // 64-byte granularity up to 256 KiB, longer records share the first bucket
-
 __device__ __forceinline__ uint32_t len_bucket(int64_t len)
 {
     const int64_t b = (len + 63) >> 6;
@@ -95,31 +95,116 @@ __global__ void __launch_bounds__(256) len_hist_kernel(const int64_t *__restrict
         if (s_h[k]) atomicAdd(&hist[k], s_h[k]);
 }
 
-__global__ void __launch_bounds__(1024) len_scan_kernel(uint32_t *__restrict__ hist)   // in place: counts -> cursors
+// One CTA of 1024 threads, 4 buckets per thread: counts -> exclusive cursors (in place), plus the divergence
+// estimate of INPUT order, hist[LEN_BUCKETS] = 256 * E[longest of 32 records] / E[record] in 64-byte blocks with
+// the records taken as iid: P(max <= b) = F(b)^32.  (A single thread walking the 4096 buckets took 0.1-0.4 ms.)
+__global__ void __launch_bounds__(1024) len_scan_kernel(uint32_t *__restrict__ hist)
 {
-    __shared__ uint32_t s[LEN_BUCKETS];
-    for (uint32_t k = threadIdx.x; k < LEN_BUCKETS; k += 1024) s[k] = hist[k];
+    __shared__ uint32_t s_warp[32], s_total;
+    __shared__ float s_emax, s_sumb;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) { s_emax = 0.f; s_sumb = 0.f; }
+    uint32_t c[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) c[j] = hist[4 * t + j];
+    const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (uint32_t k = 0; k < LEN_BUCKETS; k++) { const uint32_t c = s[k]; s[k] = run; run += c; }
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (uint32_t)d) wi += v;
+        }
+        s_warp[lane] = wi - w;   // exclusive warp bases; lane 31's inclusive value is the total
+        if (lane == 31) s_total = wi;
     }
     __syncthreads();
-    for (uint32_t k = threadIdx.x; k < LEN_BUCKETS; k += 1024) hist[k] = s[k];
+    const uint32_t total = s_total;
+    uint32_t excl = s_warp[warp] + incl - mine;
+    float emax = 0.f, sumb = 0.f;
+    const float inv = total ? 1.f / (float)total : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t k = 4 * t + j;
+        hist[k] = excl;
+        if (c[j]) {
+            // bucket k holds the records of b = LEN_BUCKETS-1-k blocks; records no longer than that: total - excl
+            float f = (float)(total - excl) * inv, fp = (float)(total - excl - c[j]) * inv;
+            f *= f; f *= f; f *= f; f *= f; f *= f;
+            fp *= fp; fp *= fp; fp *= fp; fp *= fp; fp *= fp;
+            const float b = (float)(LEN_BUCKETS - 1 - k);
+            emax += b * (f - fp);
+            sumb += b * (float)c[j];
+        }
+        excl += c[j];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        emax += __shfl_xor_sync(0xffffffffu, emax, d);
+        sumb += __shfl_xor_sync(0xffffffffu, sumb, d);
+    }
+    if (lane == 0 && (emax != 0.f || sumb != 0.f)) { atomicAdd(&s_emax, emax); atomicAdd(&s_sumb, sumb); }
+    __syncthreads();
+    if (t == 0) {
+        const float mean_b = total ? s_sumb * inv : 0.f;
+        hist[LEN_BUCKETS] = mean_b > 0.f ? (uint32_t)(s_emax / mean_b * 256.f) : 256u;
+    }
 }
 
+// Each CTA ranks a contiguous run of SCATTER_PER_CTA records inside shared memory and reserves one range per
+// bucket it met with a single global atomic.  (One global atomic per record serialises on the few hot buckets:
+// 0.3-0.5 ms for a million records of nearly equal length.)
+constexpr uint32_t SCATTER_PER_THREAD = 8, SCATTER_PER_CTA = 256 * SCATTER_PER_THREAD;
 __global__ void __launch_bounds__(256) len_scatter_kernel(const int64_t *__restrict__ offs, size_t n,
-                                                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ perm)
+                                                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ perm,
+                                                          uint32_t identity_below_q8)
 {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        perm[atomicAdd(&cursor[len_bucket(offs[i + 1] - offs[i])], 1u)] = (uint32_t)i;
+    __shared__ uint32_t s_cnt[LEN_BUCKETS];    // records of this CTA per bucket, then the reserved base
+    if (cursor[LEN_BUCKETS] < identity_below_q8) {   // input order wastes too little to pay for scattered reads
+        for (uint32_t j = 0; j < SCATTER_PER_THREAD; j++) {
+            const size_t i = (size_t)blockIdx.x * SCATTER_PER_CTA + j * 256 + threadIdx.x;
+            if (i < n) perm[i] = (uint32_t)i;
+        }
+        return;
+    }
+    for (uint32_t k = threadIdx.x; k < LEN_BUCKETS; k += 256) s_cnt[k] = 0;
+    __syncthreads();
+    const size_t first = (size_t)blockIdx.x * SCATTER_PER_CTA;
+    uint32_t bucket[SCATTER_PER_THREAD], rank[SCATTER_PER_THREAD];
+#pragma unroll
+    for (uint32_t j = 0; j < SCATTER_PER_THREAD; j++) {
+        const size_t i = first + j * 256 + threadIdx.x;
+        if (i < n) {
+            bucket[j] = len_bucket(offs[i + 1] - offs[i]);
+            rank[j] = atomicAdd(&s_cnt[bucket[j]], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < LEN_BUCKETS; k += 256) {
+        const uint32_t c = s_cnt[k];
+        if (c) s_cnt[k] = atomicAdd(&cursor[k], c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t j = 0; j < SCATTER_PER_THREAD; j++) {
+        const size_t i = first + j * 256 + threadIdx.x;
+        if (i < n) perm[s_cnt[bucket[j]] + rank[j]] = (uint32_t)i;
+    }
 }
 
-size_t length_sort_bytes(size_t n) { return (n * 4 + 255) / 256 * 256 + LEN_BUCKETS * 4; }
+size_t length_sort_bytes(size_t n) { return (n * 4 + 255) / 256 * 256 + (LEN_BUCKETS + 64) * 4; }
 
-// perm_and_tmp: length_sort_bytes(n) bytes; perm = first n uint32
-cudaError_t launch_length_sort(const int64_t *offs, size_t n, void *perm_and_tmp, cudaStream_t st)
+// perm_and_tmp: length_sort_bytes(n) bytes; perm = first n uint32.  identity_below_q8: when the divergence
+// estimate of input order (x256) is below it, perm is the identity (input order is kept).
+cudaError_t launch_length_sort(const int64_t *offs, size_t n, void *perm_and_tmp, uint32_t identity_below_q8, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     uint32_t *perm = static_cast<uint32_t *>(perm_and_tmp);
@@ -130,7 +215,7 @@ cudaError_t launch_length_sort(const int64_t *offs, size_t n, void *perm_and_tmp
     if (blocks > 148u * 8u) blocks = 148u * 8u;
     len_hist_kernel<<<(unsigned)blocks, 256, 0, st>>>(offs, n, hist);
     len_scan_kernel<<<1, 1024, 0, st>>>(hist);
-    len_scatter_kernel<<<(unsigned)blocks, 256, 0, st>>>(offs, n, hist, perm);
+    len_scatter_kernel<<<(unsigned)((n + SCATTER_PER_CTA - 1) / SCATTER_PER_CTA), 256, 0, st>>>(offs, n, hist, perm, identity_below_q8);
     g_launches += 3;
     return cudaGetLastError();
 }

@@ -25,11 +25,11 @@ constexpr uint32_t NORM_BLK = 4096;
 inline size_t norm_blocks(size_t total_bytes) { return total_bytes / NORM_BLK + 1; }
 
 // Direct path: one thread per record straight from global memory.
-// perm (may be null) = record indices in descending length order from launch_length_sort.
+// perm (may be null) = the order in which the records are visited, from launch_length_sort.
 cudaError_t launch_hash_direct(int algo, bool upper, const uint8_t *res, const int64_t *offs, size_t n,
                                uint8_t *out, const uint32_t *perm, cudaStream_t st);
 size_t length_sort_bytes(size_t n);
-cudaError_t launch_length_sort(const int64_t *offs, size_t n, void *perm_and_tmp, cudaStream_t st);
+cudaError_t launch_length_sort(const int64_t *offs, size_t n, void *perm_and_tmp, uint32_t identity_below_q8, cudaStream_t st);
 
 // Tile path (tile.cu): CTA-staged shared-memory tiles of 128 records, one thread per record.  `mask` has
 // bit a set for every algorithm to compute; more than one bit is allowed only inside tile_fast_mask()
