@@ -76,3 +76,13 @@ def test_c4_long_reads(shb, oracle):
 def test_c5_variable_all_algorithms(shb, oracle):
     from seqhasher_b200.binding import ALGO_NAMES
     _check(shb, oracle, 300_000, (30, 3000), ALGO_NAMES, 3, 0xC5, shb.FLAG_NO_LENGTH_SORT, sample=3000)
+
+
+@pytest.mark.parametrize("lens", [(800, 1200), 1000, (2000, 8000)], ids=["narrow", "uniform", "2k-8k"])
+def test_visiting_order_policy_never_changes_a_digest(shb, oracle, lens):
+    """The direct kernels visit the records in length-sorted or input order depending on a divergence estimate made
+    on the device (narrow spread: sorted for sha1/sha3/blake3/k12 only; uniform: identity permutation; 2-8 kB: the
+    multiply-based hashes keep input order).  Whatever the order, digests land at the record's own index."""
+    from seqhasher_b200.binding import ALGO_NAMES
+    _check(shb, oracle, 120_000, lens, ALGO_NAMES, 1, 0x50 + (lens if isinstance(lens, int) else lens[0]) % 7, shb.FLAG_NO_LENGTH_SORT,
+           sample=1500)
