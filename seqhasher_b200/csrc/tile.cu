@@ -77,6 +77,9 @@ __device__ __forceinline__ uint32_t strip_to_scratch(const uint8_t *__restrict__
     return j;
 }
 
+constexpr uint32_t bit(int a) { return 1u << a; }
+constexpr uint32_t INT_BOUND_MASK = bit(A_SHA1) | bit(A_MD5) | bit(A_SHA3) | bit(A_K12) | bit(A_BLAKE3);
+
 // STRIP fuses the whitespace strip (seqhasher.go:246) into the tile pass without a second look at the data:
 // the readers OR a "byte < 0x21" test into a flag while the record is being hashed (for a fused set with
 // upper-casing the flag comes from the in-place upper pass instead); only a record that really holds such a
@@ -90,12 +93,19 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     constexpr bool MULTI = (MASK & (MASK - 1)) != 0;
     constexpr bool INPLACE = MULTI && UPPER;          // tile upper-cased in place by a cooperative pass
     constexpr bool SPECULATE = STRIP && !INPLACE;     // whitespace candidates detected by the readers
+    // INT-bound hashes: the CTA hands its 128 records to the threads longest first, so that a warp's 32 records
+    // finish together (amplicon reads of 150-600 bp otherwise run every warp for its longest record)
+    constexpr bool REORDER = (MASK & ~INT_BOUND_MASK) == 0;
     extern __shared__ __align__(128) uint8_t tile[];   // cap + 32 bytes
     __shared__ uint64_t mbar;
+    __shared__ uint32_t s_bucket[REORDER ? 32 : 1];
+    __shared__ uint32_t s_rec_len[REORDER ? 128 : 1];
+    __shared__ int64_t s_rec_start[REORDER ? 128 : 1];
+    __shared__ uint8_t s_slot[REORDER ? 128 : 1];
 
     const size_t r0 = (size_t)blockIdx.x * blockDim.x;
     const size_t r1 = (r0 + blockDim.x < n) ? r0 + blockDim.x : n;
-    const size_t i = r0 + threadIdx.x;
+    size_t i = r0 + threadIdx.x;
     // every thread reads the tile bounds (same address: one broadcast transaction) and its own record
     const int64_t t_start = offs[r0], t_end = offs[r1];
     int64_t s = 0, e = 0;
@@ -103,18 +113,56 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     uint32_t len = (uint32_t)(e - s);
     const int64_t a0 = t_start & ~(int64_t)15;            // residue base is 16-byte aligned
     const int64_t span = (t_end - a0 + 15) & ~(int64_t)15;
+    const bool staged = span <= (int64_t)cap && span > 0;
+    int mixed = 0;
+
+    if (staged) {   // the copy flies while the records are being dealt out
+        if (threadIdx.x == 0) mbar_init(&mbar, 1);
+        // one barrier publishes the mbarrier and (REORDER) tells whether any warp holds records of different lengths
+        if constexpr (REORDER) mixed = __syncthreads_or(len != __shfl_sync(0xffffffffu, len, 0));
+        else __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)span;
+            mbar_expect_tx(&mbar, bytes);
+            for (uint32_t o = 0; o < bytes; o += TMA_CHUNK)
+                tma_bulk_g2s(tile + o, res + a0 + o, (bytes - o < TMA_CHUNK) ? bytes - o : TMA_CHUNK, &mbar);
+        }
+    }
+    if (REORDER) {
+        // counting sort of the CTA's records by 64-byte blocks, descending (fixed-length reads skip it)
+        if (mixed) {
+            if (threadIdx.x < 32) s_bucket[threadIdx.x] = 0;
+            __syncthreads();
+            const uint32_t blocks = (len + 63) >> 6;
+            const uint32_t key = 31u - (blocks < 31u ? blocks : 31u);
+            const uint32_t rank = atomicAdd(&s_bucket[key], 1u);
+            s_rec_len[threadIdx.x] = len;
+            s_rec_start[threadIdx.x] = s;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                const uint32_t c = s_bucket[threadIdx.x];
+                uint32_t incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (threadIdx.x >= (uint32_t)d) incl += v;
+                }
+                s_bucket[threadIdx.x] = incl - c;
+            }
+            __syncthreads();
+            s_slot[s_bucket[key] + rank] = (uint8_t)threadIdx.x;
+            __syncthreads();
+            const uint32_t mine = s_slot[threadIdx.x];
+            i = r0 + mine;
+            len = s_rec_len[mine];
+            s = s_rec_start[mine];
+        }
+    }
 
     if (span <= (int64_t)cap) {
         const uint32_t bytes = (uint32_t)span;
         const uint32_t start = (uint32_t)(s - a0);
         if (bytes) {
-            if (threadIdx.x == 0) mbar_init(&mbar, 1);
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                mbar_expect_tx(&mbar, bytes);
-                for (uint32_t o = 0; o < bytes; o += TMA_CHUNK)
-                    tma_bulk_g2s(tile + o, res + a0 + o, (bytes - o < TMA_CHUNK) ? bytes - o : TMA_CHUNK, &mbar);
-            }
             mbar_wait(&mbar, 0);
             if (INPLACE) {
                 // one cooperative pass: upper-case in place once for every hash of the set (seqhasher.go:249-251)
@@ -133,6 +181,12 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
             }
         }
         if (i < n) {
+            // The readers fetch whole words, so the tail word of the tile's last record can reach up to 7 bytes past
+            // the copied span.  Those bytes never enter a digest, but left as stale shared memory they can look like
+            // whitespace to the speculative strip and send that record through the compaction + second hash while
+            // its CTA waits (a 1.5x slowdown once the garbage happened to be small values).  Its owner, the only
+            // thread that reads them, makes them letters first.
+            if (SPECULATE && i + 1 == r1) *reinterpret_cast<uint2 *>(tile + bytes) = make_uint2(0x41414141u, 0x41414141u);
             for (int pass = 0;; pass++) {
                 SmemReader<UPPER && !MULTI, SPECULATE> r(tile, start);
                 hash_set<MASK>(r, len, i, out, rmask);
@@ -154,7 +208,6 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     }
 }
 
-constexpr uint32_t bit(int a) { return 1u << a; }
 constexpr uint32_t FAST_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_CITYHASH) | bit(A_MURMUR3) | bit(A_NTHASH) |
                                bit(A_RAPIDHASH) | bit(A_RAPIDHASH32);
 constexpr uint32_t C3_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_MURMUR3);
