@@ -438,6 +438,70 @@ __device__ __forceinline__ uint64_t nt_seed(uint32_t c)
     return s;
 }
 
+// The same table for shared-memory look-ups: seeds pre-rotated by 0..3, so that a 4-byte word folds as
+// rol(h,4) ^ L3[b0] ^ L2[b1] ^ L1[b2] ^ L0[b3] with one 64-bit load per byte instead of the compare chain above
+// (about 20 ALU instructions per byte).  nt_seed_table() is evaluated at compile time into device memory.
+constexpr uint64_t nt_seed_const(uint32_t c)
+{
+    const uint32_t u = c & 0xdfu;
+    uint64_t s = 0;
+    if (u == 'A') s = NT_SEED_A;
+    if (u == 'C') s = NT_SEED_C;
+    if (u == 'G') s = NT_SEED_G;
+    if (u == 'T' || u == 'U') s = NT_SEED_T;
+    if (c < 8) {
+        if (c == 4 || c == 5) s = NT_SEED_A;
+        if (c == 7) s = NT_SEED_C;
+        if (c == 3) s = NT_SEED_G;
+        if (c == 1) s = NT_SEED_T;
+    }
+    return s;
+}
+struct NtSeedTable {
+    uint64_t v[256];
+    constexpr NtSeedTable() : v{}
+    {
+        for (uint32_t c = 0; c < 256; c++) v[c] = nt_seed_const(c);
+    }
+};
+__device__ const NtSeedTable g_nt_seed_table = NtSeedTable();
+
+constexpr uint32_t NT_LUT_WORDS = 4 * 256;   // uint64 entries: [rotation k][byte]
+
+// cooperative fill by the whole CTA (coalesced reads of the 2 KiB seed table); the caller synchronises
+__device__ __forceinline__ void nt_fill_lut(uint64_t *lut)
+{
+    for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) {
+        const uint64_t s = g_nt_seed_table.v[c];
+        lut[c] = s;
+        lut[256 + c] = rotl64(s, 1);
+        lut[512 + c] = rotl64(s, 2);
+        lut[768 + c] = rotl64(s, 3);
+    }
+}
+
+// fold 4 bytes (memory order b0..b3) into h
+__device__ __forceinline__ uint64_t nt_fold4(uint64_t h, uint32_t w, const uint64_t *lut)
+{
+    return rotl64(h, 4) ^ lut[768 + (w & 0xffu)] ^ lut[512 + ((w >> 8) & 0xffu)] ^ lut[256 + ((w >> 16) & 0xffu)] ^ lut[w >> 24];
+}
+
+template <class R>
+__device__ __forceinline__ uint64_t nthash_record_lut(const R &r, uint32_t len, const uint64_t *lut)
+{
+    uint64_t h = 0;
+    uint32_t p = 0;
+    for (; p + 4 <= len; p += 4) h = nt_fold4(h, r.u32(p), lut);
+    if (p < len) {
+        uint32_t w = r.u32(p);
+        for (; p < len; p++) {
+            h = rotl64(h, 1) ^ lut[w & 0xffu];
+            w >>= 8;
+        }
+    }
+    return h;
+}
+
 // forward hash of the whole record: h = rol(h,1) ^ seed[c] over all bytes
 template <class R>
 __device__ __forceinline__ uint64_t nthash_record(const R &r, uint32_t len)

@@ -16,27 +16,6 @@ namespace shb {
 
 // ------------------------------------------------------------------------------------------- ntHash
 
-// seed LUTs pre-rotated by 3,2,1,0: a 4-byte word folds as rol(h,4) ^ L3[b0] ^ L2[b1] ^ L1[b2] ^ L0[b3]
-struct NtLut {
-    uint64_t rot[4][256];
-};
-
-__device__ __forceinline__ void nt_fill_lut(NtLut *lut)
-{
-    for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) {
-        const uint64_t s = nt_seed(c);
-#pragma unroll
-        for (int k = 0; k < 4; k++) lut->rot[k][c] = k ? rotl64(s, k) : s;
-    }
-}
-
-// fold 4 bytes (memory order b0..b3) into h
-__device__ __forceinline__ uint64_t nt_fold4(uint64_t h, uint32_t w, const NtLut *lut)
-{
-    return rotl64(h, 4) ^ lut->rot[3][w & 0xffu] ^ lut->rot[2][(w >> 8) & 0xffu] ^ lut->rot[1][(w >> 16) & 0xffu] ^
-           lut->rot[0][w >> 24];
-}
-
 __device__ __forceinline__ uint64_t rotl64v(uint64_t x, uint32_t r)   // r in 0..63, run-time
 {
     r &= 63u;
@@ -58,8 +37,8 @@ __global__ void __launch_bounds__(256) nthash_warp_kernel(const uint8_t *__restr
                                                           const int64_t *__restrict__ offs, size_t n,
                                                           uint8_t *__restrict__ out)
 {
-    __shared__ NtLut lut;
-    nt_fill_lut(&lut);
+    __shared__ uint64_t lut[NT_LUT_WORDS];   // pre-rotated seed look-ups, hash_fast.cuh
+    nt_fill_lut(lut);
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -86,7 +65,7 @@ __global__ void __launch_bounds__(256) nthash_warp_kernel(const uint8_t *__restr
             }
             uint64_t t = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) t = nt_fold4(t, UPPER ? upper4(w[k]) : w[k], &lut);
+            for (int k = 0; k < 4; k++) t = nt_fold4(t, UPPER ? upper4(w[k]) : w[k], lut);
             // t = XOR_j rol(seed[b_j], 15 - j); position pos+j carries rotation (len-1-pos-j) mod 64
             acc ^= rotl64v(t, (uint32_t)((len - 16 - pos) & 63));
         }

@@ -20,32 +20,36 @@ struct OutPtrs {
 };
 
 template <uint32_t MASK, int ALGO, class R>
-__device__ __forceinline__ void hash_if(const R &r, uint32_t len, size_t i, const OutPtrs &out, uint32_t rmask)
+__device__ __forceinline__ void hash_if(const R &r, uint32_t len, size_t i, const OutPtrs &out, uint32_t rmask,
+                                        const uint64_t *nt_lut)
 {
     if ((MASK >> ALGO) & 1u) {
         if ((rmask >> ALGO) & 1u) {
             uint8_t *o = out.p[ALGO] + i * digest_size(ALGO);
             if (len == 0) zero_digest<ALGO>(o);   // empty-sequence rule, seqhasher.go:292-295
+            else if (ALGO == A_NTHASH && nt_lut) store_be64(o, nthash_record_lut(r, len, nt_lut));   // shared-memory seeds
             else hash_one<ALGO>(r, len, o);
         }
     }
 }
 
+// nt_lut: the CTA's pre-rotated ntHash seed table in shared memory (null on paths that did not build one)
 template <uint32_t MASK, class R>
-__device__ __forceinline__ void hash_set(const R &r, uint32_t len, size_t i, const OutPtrs &out, uint32_t rmask)
+__device__ __forceinline__ void hash_set(const R &r, uint32_t len, size_t i, const OutPtrs &out, uint32_t rmask,
+                                         const uint64_t *nt_lut = nullptr)
 {
-    hash_if<MASK, A_SHA1>(r, len, i, out, rmask);
-    hash_if<MASK, A_SHA3>(r, len, i, out, rmask);
-    hash_if<MASK, A_MD5>(r, len, i, out, rmask);
-    hash_if<MASK, A_XXHASH>(r, len, i, out, rmask);
-    hash_if<MASK, A_XXH3>(r, len, i, out, rmask);
-    hash_if<MASK, A_CITYHASH>(r, len, i, out, rmask);
-    hash_if<MASK, A_MURMUR3>(r, len, i, out, rmask);
-    hash_if<MASK, A_NTHASH>(r, len, i, out, rmask);
-    hash_if<MASK, A_BLAKE3>(r, len, i, out, rmask);
-    hash_if<MASK, A_K12>(r, len, i, out, rmask);
-    hash_if<MASK, A_RAPIDHASH>(r, len, i, out, rmask);
-    hash_if<MASK, A_RAPIDHASH32>(r, len, i, out, rmask);
+    hash_if<MASK, A_SHA1>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_SHA3>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_MD5>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_XXHASH>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_XXH3>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_CITYHASH>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_MURMUR3>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_NTHASH>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_BLAKE3>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_K12>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_RAPIDHASH>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_RAPIDHASH32>(r, len, i, out, rmask, nt_lut);
 }
 
 constexpr uint32_t TMA_CHUNK = 32768;   // one bulk copy moves at most this many bytes
@@ -78,7 +82,6 @@ __device__ __forceinline__ uint32_t strip_to_scratch(const uint8_t *__restrict__
 }
 
 constexpr uint32_t bit(int a) { return 1u << a; }
-constexpr uint32_t INT_BOUND_MASK = bit(A_SHA1) | bit(A_MD5) | bit(A_SHA3) | bit(A_K12) | bit(A_BLAKE3);
 
 // STRIP fuses the whitespace strip (seqhasher.go:246) into the tile pass without a second look at the data:
 // the readers OR a "byte < 0x21" test into a flag while the record is being hashed (for a fused set with
@@ -93,11 +96,14 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     constexpr bool MULTI = (MASK & (MASK - 1)) != 0;
     constexpr bool INPLACE = MULTI && UPPER;          // tile upper-cased in place by a cooperative pass
     constexpr bool SPECULATE = STRIP && !INPLACE;     // whitespace candidates detected by the readers
-    // INT-bound hashes: the CTA hands its 128 records to the threads longest first, so that a warp's 32 records
-    // finish together (amplicon reads of 150-600 bp otherwise run every warp for its longest record)
-    constexpr bool REORDER = (MASK & ~INT_BOUND_MASK) == 0;
+    // The CTA hands its 128 records to the threads longest first, so that a warp's 32 records finish together
+    // (amplicon reads of 100-600 bp otherwise run every warp for its longest record: x1.3-1.6 for the INT-bound
+    // hashes, x1.1-1.5 for the HBM-bound ones; fixed-length reads pay one shuffle and the barrier's vote, <= 2 %).
+    constexpr bool REORDER = true;
+    constexpr bool NT = (MASK >> A_NTHASH) & 1u;
     extern __shared__ __align__(128) uint8_t tile[];   // cap + 32 bytes
     __shared__ uint64_t mbar;
+    __shared__ uint64_t s_nt[NT ? NT_LUT_WORDS : 1];   // ntHash seeds, filled before the barrier below
     __shared__ uint32_t s_bucket[REORDER ? 32 : 1];
     __shared__ uint32_t s_rec_len[REORDER ? 128 : 1];
     __shared__ int64_t s_rec_start[REORDER ? 128 : 1];
@@ -116,6 +122,7 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     const bool staged = span <= (int64_t)cap && span > 0;
     int mixed = 0;
 
+    if (NT && staged) nt_fill_lut(s_nt);
     if (staged) {   // the copy flies while the records are being dealt out
         if (threadIdx.x == 0) mbar_init(&mbar, 1);
         // one barrier publishes the mbarrier and (REORDER) tells whether any warp holds records of different lengths
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
             if (SPECULATE && i + 1 == r1) *reinterpret_cast<uint2 *>(tile + bytes) = make_uint2(0x41414141u, 0x41414141u);
             for (int pass = 0;; pass++) {
                 SmemReader<UPPER && !MULTI, SPECULATE> r(tile, start);
-                hash_set<MASK>(r, len, i, out, rmask);
+                hash_set<MASK>(r, len, i, out, rmask, NT ? s_nt : nullptr);
                 if (!SPECULATE || pass == 1 || !r.saw_ws_candidate()) break;
                 len = strip_in_smem(tile, start, len);   // rare: compact this record, hash it again
             }
