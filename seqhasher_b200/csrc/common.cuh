@@ -36,11 +36,15 @@ static __constant__ uint32_t c_one = 1u;
 __device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t y) { return x * c_one + y; }
 
 // ASCII upper-casing of 4 packed bytes (a-z -> A-Z, everything else untouched, bytes >= 0x80 too).
+// FMA: the two adds as IMADs on the FMA pipe — every kernel that upper-cases while hashing is bound by the ALU pipe
+// or by issue slots, and this is input preparation off the hash's dependency chain (C2: sha1 -1.8 %, md5 -2 %,
+// xxh3 -2 ... -4 %).  The one exception measured is SHA-1 with the whitespace detector (+1.9 %), which passes false.
+template <bool FMA = true>
 __device__ __forceinline__ uint32_t upper4(uint32_t x)
 {
     uint32_t y = x & 0x7f7f7f7fu;
-    uint32_t ge_a = y + 0x1f1f1f1fu;   // bit7 set  <=>  (b & 0x7f) >= 'a'
-    uint32_t gt_z = y + 0x05050505u;   // bit7 set  <=>  (b & 0x7f) >  'z'
+    uint32_t ge_a = FMA ? fma_add(y, 0x1f1f1f1fu) : y + 0x1f1f1f1fu;   // bit7 set  <=>  (b & 0x7f) >= 'a'
+    uint32_t gt_z = FMA ? fma_add(y, 0x05050505u) : y + 0x05050505u;   // bit7 set  <=>  (b & 0x7f) >  'z'
     uint32_t m = ge_a & ~gt_z & ~x & 0x80808080u;
     return x ^ (m >> 2);
 }
@@ -50,7 +54,7 @@ __device__ __forceinline__ bool is_ws(uint32_t c) { return c == 0x20u || (c - 9u
 
 // NC = true reads through the non-coherent path (ld.global.nc); NC = false is for buffers written earlier
 // in the same kernel (the strip scratch).
-template <bool UPPER, bool NC = true>
+template <bool UPPER, bool NC = true, bool FMA_PREP = true>
 struct GlobalReader {
     static __device__ __forceinline__ uint32_t ld(const uint32_t *p) { return NC ? __ldg(p) : *p; }
     const uint32_t *w;   // aligned-down word pointer of the record start
@@ -70,14 +74,14 @@ struct GlobalReader {
     {
         const uint32_t *q = w + (off >> 2);
         uint32_t v = __byte_perm(ld(q), ld(q + 1), besel);
-        return UPPER ? upper4(v) : v;
+        return UPPER ? upper4<FMA_PREP>(v) : v;
     }
     // 32-bit LE word at byte offset `off` (multiple of 4) of the record
     __device__ __forceinline__ uint32_t u32(uint32_t off) const
     {
         const uint32_t *q = w + (off >> 2);
         uint32_t v = __funnelshift_r(ld(q), ld(q + 1), sh);
-        return UPPER ? upper4(v) : v;
+        return UPPER ? upper4<FMA_PREP>(v) : v;
     }
     // 32-bit LE word at ANY byte offset
     __device__ __forceinline__ uint32_t u32x(uint32_t off) const
@@ -85,7 +89,7 @@ struct GlobalReader {
         uint32_t a = off + bo;
         const uint32_t *q = w + (a >> 2);
         uint32_t v = __funnelshift_r(ld(q), ld(q + 1), (a & 3) * 8);
-        return UPPER ? upper4(v) : v;
+        return UPPER ? upper4<FMA_PREP>(v) : v;
     }
     __device__ __forceinline__ uint64_t u64(uint32_t off) const { return mk64(u32(off), u32(off + 4)); }
     __device__ __forceinline__ uint64_t u64x(uint32_t off) const
@@ -95,7 +99,7 @@ struct GlobalReader {
         uint32_t w0 = ld(q), w1 = ld(q + 1), w2 = ld(q + 2);
         uint32_t s = (a & 3) * 8;
         uint32_t lo = __funnelshift_r(w0, w1, s), hi = __funnelshift_r(w1, w2, s);
-        if (UPPER) { lo = upper4(lo); hi = upper4(hi); }
+        if (UPPER) { lo = upper4<FMA_PREP>(lo); hi = upper4<FMA_PREP>(hi); }
         return mk64(lo, hi);
     }
     __device__ __forceinline__ uint32_t u8(uint32_t off) const { return u32x(off) & 0xffu; }
@@ -126,7 +130,7 @@ struct GlobalReader {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 uint32_t t = BE ? __byte_perm(x[i], x[i + 1], besel) : __funnelshift_r(x[i], x[i + 1], sh);
-                o[i] = UPPER ? upper4(t) : t;
+                o[i] = UPPER ? upper4<FMA_PREP>(t) : t;
             }
             c = n;
         }
@@ -149,7 +153,8 @@ struct GlobalReader {
 
 // DETECT = true also ORs a "some byte < 0x21" test of every word handed out into `wsf` (bit 7 of a byte
 // set => a whitespace candidate was read): the speculative whitespace detection of the fused strip.
-template <bool UPPER, bool DETECT = false>
+// FMA_PREP: the adds of the upper-casing and of that test as IMADs (see upper4).
+template <bool UPPER, bool DETECT = false, bool FMA_PREP = true>
 struct SmemReader {
     const uint32_t *w;
     uint32_t bo, sh, besel;
@@ -164,8 +169,8 @@ struct SmemReader {
     }
     __device__ __forceinline__ uint32_t fin(uint32_t v) const
     {
-        if (DETECT) wsf |= (v - 0x21212121u) & ~v;
-        return UPPER ? upper4(v) : v;
+        if (DETECT) wsf |= (FMA_PREP ? fma_add(v, 0xdededfdfu) : v - 0x21212121u) & ~v;   // bit 7 of a byte <=> byte < 0x21
+        return UPPER ? upper4<FMA_PREP>(v) : v;
     }
     __device__ __forceinline__ bool saw_ws_candidate() const { return DETECT && (wsf & 0x80808080u) != 0; }
     __device__ __forceinline__ uint32_t u32be(uint32_t off) const

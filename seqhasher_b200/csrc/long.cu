@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128) k12_leaves_kernel(const uint8_t *__restri
     const int64_t s = offs[i];
     const uint32_t len = (uint32_t)(offs[i + 1] - s);
     const uint32_t c = (uint32_t)(g - leaf_base[i]) + 1u;
-    GlobalReader<UPPER> r(res, s);
+    GlobalReader<UPPER, true, false> r(res, s);   // k12: upper-casing adds stay on the ALU pipe (measured)
     uint64_t cv[4];
     kt128_leaf_cv(r, len, c, cv);
     uint64_t *dst = cvs + g * 4;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(128) k12_final_kernel(const uint8_t *__restric
         zero_digest<A_K12>(o);
         return;
     }
-    GlobalReader<UPPER> r(res, s);
+    GlobalReader<UPPER, true, false> r(res, s);   // k12: upper-casing adds stay on the ALU pipe (measured)
     if (len < 8192) {
         kt128_record(r, len, o);
         return;

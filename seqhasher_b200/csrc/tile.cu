@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     // (amplicon reads of 100-600 bp otherwise run every warp for its longest record: x1.3-1.6 for the INT-bound
     // hashes, x1.1-1.5 for the HBM-bound ones; fixed-length reads pay one shuffle and the barrier's vote, <= 2 %).
     constexpr bool REORDER = true;
+    // input preparation (upper-casing, whitespace test) on the FMA pipe — everywhere except SHA-1 with the detector
+    constexpr bool FMA_PREP = !(SPECULATE && ((MASK >> A_SHA1) & 1u)) && !((MASK >> A_K12) & 1u);   // k12: 168-216 registers, -4 %
     constexpr bool NT = (MASK >> A_NTHASH) & 1u;
     extern __shared__ __align__(128) uint8_t tile[];   // cap + 32 bytes
     __shared__ uint64_t mbar;
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
             // thread that reads them, makes them letters first.
             if (SPECULATE && i + 1 == r1) *reinterpret_cast<uint2 *>(tile + bytes) = make_uint2(0x41414141u, 0x41414141u);
             for (int pass = 0;; pass++) {
-                SmemReader<UPPER && !MULTI, SPECULATE> r(tile, start);
+                SmemReader<UPPER && !MULTI, SPECULATE, FMA_PREP> r(tile, start);
                 hash_set<MASK>(r, len, i, out, rmask, NT ? s_nt : nullptr);
                 if (!SPECULATE || pass == 1 || !r.saw_ws_candidate()) break;
                 len = strip_in_smem(tile, start, len);   // rare: compact this record, hash it again
@@ -206,10 +208,10 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
         if (STRIP) {
             len = strip_to_scratch(res, strip_scratch, s, len);
             if (out_len) out_len[i] = len;
-            GlobalReader<UPPER, false> r(strip_scratch, s);   // written by this thread just above
+            GlobalReader<UPPER, false, FMA_PREP> r(strip_scratch, s);   // written by this thread just above
             hash_set<MASK>(r, len, i, out, rmask);
         } else {
-            GlobalReader<UPPER> r(res, s);
+            GlobalReader<UPPER, true, FMA_PREP> r(res, s);
             hash_set<MASK>(r, len, i, out, rmask);
         }
     }
