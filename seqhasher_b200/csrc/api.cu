@@ -126,6 +126,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         // BLAKE3 and K12 only pay off for multi-kilobyte records (below, the length-sorted direct kernels win).
         const bool long_ok = n && !(flags & (SHB_FLAG_FORCE_DIRECT | SHB_FLAG_NO_LONG_PATH));
         const bool long_mode = long_ok && mean >= 4096;
+        const size_t nt_warp_min = 2560;   // below: thread per record with the shared-memory seed table (x1.4-1.9)
         // Thread-per-record kernels can walk the records in descending length order (counting sort of the indices by
         // 64-byte blocks) so that a warp's 32 records finish together.  Whether that pays is decided on the device
         // (one order per batch: the lowest threshold among the requested algorithms; below it the permutation is the
@@ -139,7 +140,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         //                                  x0.6-0.8 at 2-8 kB, x0.3-0.5 at 10-50 kB)
         const uint32_t kHeavy = (1u << SHB_SHA3) | (1u << SHB_BLAKE3) | (1u << SHB_K12);
         const uint32_t kStream = (1u << SHB_XXHASH) | (1u << SHB_CITYHASH) | (1u << SHB_MURMUR3) | (1u << SHB_RAPIDHASH) |
-                                 (1u << SHB_RAPIDHASH32);
+                                 (1u << SHB_RAPIDHASH32) | (1u << SHB_NTHASH);
         const uint32_t kSortMask = kHeavy | (mean < 16384 ? (1u << SHB_SHA1) | (1u << SHB_MD5) : 0u) | (mean < 2560 ? kStream : 0u);
         auto min_waste_q8 = [&](int a) -> uint32_t {   // x256
             if (kStream >> a & 1u) return 358u;        // 1.40
@@ -157,7 +158,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         }
         for (int a = 0; a < SHB_N_ALGOS; a++) {
             if (!(want >> a & 1u)) continue;
-            if (long_ok && a == SHB_NTHASH) {
+            if (long_ok && a == SHB_NTHASH && mean >= nt_warp_min) {
                 CU(shb::launch_nthash_long(fused_upper, res, offs, n, slot_of[a], st));
             } else if (long_ok && a == SHB_XXH3) {
                 CU(shb::launch_xxh3_long(fused_upper, res, offs, n, slot_of[a], st));

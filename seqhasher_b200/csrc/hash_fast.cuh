@@ -468,34 +468,73 @@ __device__ const NtSeedTable g_nt_seed_table = NtSeedTable();
 
 constexpr uint32_t NT_LUT_WORDS = 4 * 256;   // uint64 entries: [rotation k][byte]
 
+// The entry of byte c sits at index c ^ (c >> 5): 64-bit entries 16 apart share their two banks, and 'A'/'a',
+// 'C'/'c', ... are exactly 32 apart, so soft-masked (mixed-case) sequence would make every look-up a 2-way bank
+// conflict.  With the swizzle the ten bytes ACGTN/acgtn land in ten different bank pairs.  SWZ is on when the kernel
+// sees the bytes as they are (case-sensitive mode); after upper-casing there is nothing to separate and the two
+// extra instructions per word would only cost (3-6 %).
+template <bool SWZ>
+__device__ __forceinline__ uint32_t nt_swz(uint32_t c) { return SWZ ? c ^ (c >> 5) : c; }
+
 // cooperative fill by the whole CTA (coalesced reads of the 2 KiB seed table); the caller synchronises
+template <bool SWZ>
 __device__ __forceinline__ void nt_fill_lut(uint64_t *lut)
 {
     for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) {
         const uint64_t s = g_nt_seed_table.v[c];
-        lut[c] = s;
-        lut[256 + c] = rotl64(s, 1);
-        lut[512 + c] = rotl64(s, 2);
-        lut[768 + c] = rotl64(s, 3);
+        const uint32_t k = nt_swz<SWZ>(c);
+        lut[k] = s;
+        lut[256 + k] = rotl64(s, 1);
+        lut[512 + k] = rotl64(s, 2);
+        lut[768 + k] = rotl64(s, 3);
     }
 }
 
 // fold 4 bytes (memory order b0..b3) into h
+template <bool SWZ>
 __device__ __forceinline__ uint64_t nt_fold4(uint64_t h, uint32_t w, const uint64_t *lut)
 {
+    if (SWZ) w ^= (w >> 5) & 0x07070707u;   // nt_swz on the four bytes at once
     return rotl64(h, 4) ^ lut[768 + (w & 0xffu)] ^ lut[512 + ((w >> 8) & 0xffu)] ^ lut[256 + ((w >> 16) & 0xffu)] ^ lut[w >> 24];
 }
 
-template <class R>
+template <bool SWZ, class R>
 __device__ __forceinline__ uint64_t nthash_record_lut(const R &r, uint32_t len, const uint64_t *lut)
 {
     uint64_t h = 0;
     uint32_t p = 0;
-    for (; p + 4 <= len; p += 4) h = nt_fold4(h, r.u32(p), lut);
+    for (; p + 4 <= len; p += 4) h = nt_fold4<SWZ>(h, r.u32(p), lut);
     if (p < len) {
         uint32_t w = r.u32(p);
         for (; p < len; p++) {
-            h = rotl64(h, 1) ^ lut[w & 0xffu];
+            h = rotl64(h, 1) ^ lut[nt_swz<SWZ>(w & 0xffu)];
+            w >>= 8;
+        }
+    }
+    return h;
+}
+
+// the same from global memory: 16-byte groups through the reader's Stream (one 128-bit load each)
+template <bool SWZ, class R>
+__device__ __forceinline__ uint64_t nthash_record_lut_stream(const R &r, uint32_t len, const uint64_t *lut)
+{
+    uint64_t h = 0;
+    uint32_t p = 0;
+    if (len >= 16) {
+        auto in = r.stream(0);
+        do {
+            uint32_t w[4];
+            in.next(w);
+#pragma unroll
+            for (int k = 0; k < 4; k++) h = nt_fold4<SWZ>(h, w[k], lut);
+            p += 16;
+        } while (p + 16 <= len);
+    }
+    for (; p + 4 <= len; p += 4) h = nt_fold4<SWZ>(h, r.u32(p), lut);
+    if (p < len) {
+        uint32_t w = r.u32(p);
+        for (; p < len; p++) {
+            h = rotl64(h, 1) ^ lut[nt_swz<SWZ>(w & 0xffu)];
             w >>= 8;
         }
     }

@@ -23,6 +23,12 @@ __global__ void __launch_bounds__(128) hash_direct_kernel(const uint8_t *__restr
                                                           const int64_t *__restrict__ offs, size_t n,
                                                           uint8_t *__restrict__ out, const uint32_t *__restrict__ perm)
 {
+    // ntHash: pre-rotated seed table in shared memory (one 64-bit load per byte instead of a compare chain)
+    __shared__ uint64_t s_nt[ALGO == A_NTHASH ? NT_LUT_WORDS : 1];
+    if (ALGO == A_NTHASH) {
+        nt_fill_lut<!UPPER>(s_nt);
+        __syncthreads();
+    }
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
         const size_t i = perm ? (size_t)perm[t] : t;
@@ -31,6 +37,11 @@ __global__ void __launch_bounds__(128) hash_direct_kernel(const uint8_t *__restr
         uint8_t *o = out + i * digest_size(ALGO);
         if (len == 0) {   // empty-sequence rule, seqhasher.go:292-295
             zero_digest<ALGO>(o);
+            continue;
+        }
+        if (ALGO == A_NTHASH) {
+            GlobalReader<UPPER> r(res, s);
+            store_be64(o, nthash_record_lut_stream<!UPPER>(r, len, s_nt));
             continue;
         }
         // upper-casing adds on the FMA pipe, except where it measured slower (k12: 216 registers; sha1: FMA pipe busy)

@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) nthash_warp_kernel(const uint8_t *__restr
                                                           uint8_t *__restrict__ out)
 {
     __shared__ uint64_t lut[NT_LUT_WORDS];   // pre-rotated seed look-ups, hash_fast.cuh
-    nt_fill_lut(lut);
+    nt_fill_lut<false>(lut);   // long reads: no index swizzle (it costs 3 % here; uppercase data has nothing to separate)
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) nthash_warp_kernel(const uint8_t *__restr
             }
             uint64_t t = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) t = nt_fold4(t, UPPER ? upper4(w[k]) : w[k], lut);
+            for (int k = 0; k < 4; k++) t = nt_fold4<false>(t, UPPER ? upper4(w[k]) : w[k], lut);
             // t = XOR_j rol(seed[b_j], 15 - j); position pos+j carries rotation (len-1-pos-j) mod 64
             acc ^= rotl64v(t, (uint32_t)((len - 16 - pos) & 63));
         }

@@ -19,7 +19,7 @@ struct OutPtrs {
     uint8_t *p[N_ALGOS];
 };
 
-template <uint32_t MASK, int ALGO, class R>
+template <uint32_t MASK, int ALGO, bool NT_SWZ, class R>
 __device__ __forceinline__ void hash_if(const R &r, uint32_t len, size_t i, const OutPtrs &out, uint32_t rmask,
                                         const uint64_t *nt_lut)
 {
@@ -27,29 +27,29 @@ __device__ __forceinline__ void hash_if(const R &r, uint32_t len, size_t i, cons
         if ((rmask >> ALGO) & 1u) {
             uint8_t *o = out.p[ALGO] + i * digest_size(ALGO);
             if (len == 0) zero_digest<ALGO>(o);   // empty-sequence rule, seqhasher.go:292-295
-            else if (ALGO == A_NTHASH && nt_lut) store_be64(o, nthash_record_lut(r, len, nt_lut));   // shared-memory seeds
+            else if (ALGO == A_NTHASH && nt_lut) store_be64(o, nthash_record_lut<NT_SWZ>(r, len, nt_lut));   // shared-memory seeds
             else hash_one<ALGO>(r, len, o);
         }
     }
 }
 
 // nt_lut: the CTA's pre-rotated ntHash seed table in shared memory (null on paths that did not build one)
-template <uint32_t MASK, class R>
+template <uint32_t MASK, bool NT_SWZ = false, class R>
 __device__ __forceinline__ void hash_set(const R &r, uint32_t len, size_t i, const OutPtrs &out, uint32_t rmask,
                                          const uint64_t *nt_lut = nullptr)
 {
-    hash_if<MASK, A_SHA1>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_SHA3>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_MD5>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_XXHASH>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_XXH3>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_CITYHASH>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_MURMUR3>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_NTHASH>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_BLAKE3>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_K12>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_RAPIDHASH>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_RAPIDHASH32>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_SHA1, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_SHA3, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_MD5, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_XXHASH, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_XXH3, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_CITYHASH, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_MURMUR3, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_NTHASH, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_BLAKE3, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_K12, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_RAPIDHASH, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    hash_if<MASK, A_RAPIDHASH32, NT_SWZ>(r, len, i, out, rmask, nt_lut);
 }
 
 constexpr uint32_t TMA_CHUNK = 32768;   // one bulk copy moves at most this many bytes
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     const bool staged = span <= (int64_t)cap && span > 0;
     int mixed = 0;
 
-    if (NT && staged) nt_fill_lut(s_nt);
+    if (NT && staged) nt_fill_lut<!UPPER>(s_nt);
     if (staged) {   // the copy flies while the records are being dealt out
         if (threadIdx.x == 0) mbar_init(&mbar, 1);
         // one barrier publishes the mbarrier and (REORDER) tells whether any warp holds records of different lengths
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
             if (SPECULATE && i + 1 == r1) *reinterpret_cast<uint2 *>(tile + bytes) = make_uint2(0x41414141u, 0x41414141u);
             for (int pass = 0;; pass++) {
                 SmemReader<UPPER && !MULTI, SPECULATE, FMA_PREP> r(tile, start);
-                hash_set<MASK>(r, len, i, out, rmask, NT ? s_nt : nullptr);
+                hash_set<MASK, !UPPER>(r, len, i, out, rmask, NT ? s_nt : nullptr);
                 if (!SPECULATE || pass == 1 || !r.saw_ws_candidate()) break;
                 len = strip_in_smem(tile, start, len);   // rare: compact this record, hash it again
             }
