@@ -120,12 +120,11 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
                                      reinterpret_cast<int64_t *>(static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).offs_off),
                                      d_out_len, static_cast<uint8_t *>(d_scratch) + ScratchLayout(total_bytes, n).scan_off, st));
     } else {
-        // mean >= 2 KiB: the hashes with parallelism inside a record leave the thread-per-record path
-        // Kernels with parallelism inside a record.  The warp-per-record ones (ntHash 3.7x, XXH3 1.8x faster than
-        // thread-per-record already at 1.5 kB) take over as soon as tiles no longer fit; the chunk-/leaf-parallel
-        // BLAKE3 and K12 only pay off for multi-kilobyte records (below, the length-sorted direct kernels win).
+        // Kernels with parallelism inside a record pay off for multi-kilobyte records only: below the thresholds the
+        // thread-per-record kernels win (length-sorted visiting order, 128-bit stream loads, shared-memory seed table).
         const bool long_ok = n && !(flags & (SHB_FLAG_FORCE_DIRECT | SHB_FLAG_NO_LONG_PATH));
         const bool long_mode = long_ok && mean >= 4096;
+        const size_t xxh3_warp_min = 12288;   // below: thread per record, stripes through 128-bit stream loads (x1.2-1.8)
         const size_t nt_warp_min = 2560;   // below: thread per record with the shared-memory seed table (x1.4-1.9)
         // Thread-per-record kernels can walk the records in descending length order (counting sort of the indices by
         // 64-byte blocks) so that a warp's 32 records finish together.  Whether that pays is decided on the device
@@ -140,7 +139,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         //                                  x0.6-0.8 at 2-8 kB, x0.3-0.5 at 10-50 kB)
         const uint32_t kHeavy = (1u << SHB_SHA3) | (1u << SHB_BLAKE3) | (1u << SHB_K12);
         const uint32_t kStream = (1u << SHB_XXHASH) | (1u << SHB_CITYHASH) | (1u << SHB_MURMUR3) | (1u << SHB_RAPIDHASH) |
-                                 (1u << SHB_RAPIDHASH32) | (1u << SHB_NTHASH);
+                                 (1u << SHB_RAPIDHASH32) | (1u << SHB_NTHASH) | (1u << SHB_XXH3);
         const uint32_t kSortMask = kHeavy | (mean < 16384 ? (1u << SHB_SHA1) | (1u << SHB_MD5) : 0u) | (mean < 2560 ? kStream : 0u);
         auto min_waste_q8 = [&](int a) -> uint32_t {   // x256
             if (kStream >> a & 1u) return 358u;        // 1.40
@@ -160,7 +159,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
             if (!(want >> a & 1u)) continue;
             if (long_ok && a == SHB_NTHASH && mean >= nt_warp_min) {
                 CU(shb::launch_nthash_long(fused_upper, res, offs, n, slot_of[a], st));
-            } else if (long_ok && a == SHB_XXH3) {
+            } else if (long_ok && a == SHB_XXH3 && mean >= xxh3_warp_min) {
                 CU(shb::launch_xxh3_long(fused_upper, res, offs, n, slot_of[a], st));
             } else if (long_mode && mean >= 8192 && a == SHB_K12 && d_scratch) {
                 ScratchLayout L(total_bytes, n);

@@ -143,6 +143,26 @@ __device__ __forceinline__ void xxh3_accumulate(uint64_t (&acc)[8], const R &r, 
     }
 }
 
+// one 64-byte stripe taken from the reader's sequential stream (four 16-byte groups)
+template <class S>
+__device__ __forceinline__ void xxh3_accumulate_stream(uint64_t (&acc)[8], S &in, uint32_t soff)
+{
+    uint64_t d[8];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        uint32_t w[4];
+        in.next(w);
+        d[2 * g] = mk64(w[0], w[1]);
+        d[2 * g + 1] = mk64(w[2], w[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t k = d[i] ^ xsec(soff + 8 * i);
+        acc[i ^ 1] += d[i];
+        acc[i] += (uint64_t)(uint32_t)k * (uint64_t)(uint32_t)(k >> 32);
+    }
+}
+
 template <class R>
 __device__ __forceinline__ uint64_t xxh3_record(const R &r, uint32_t n)
 {
@@ -191,9 +211,10 @@ __device__ __forceinline__ uint64_t xxh3_record(const R &r, uint32_t n)
     }
     uint64_t acc[8] = {XP32_3, XP64_1, XP64_2, XP64_3, XP64_4, XP32_2, XP64_5, XP32_1};
     const uint32_t nblocks = (n - 1) >> 10;
+    auto in = r.stream(0);   // the stripes are consecutive from offset 0: one 128-bit load per 16 bytes from global memory
     for (uint32_t b = 0; b < nblocks; b++) {
 #pragma unroll 1
-        for (uint32_t s = 0; s < 16; s++) xxh3_accumulate<false>(acc, r, (b << 10) + 64 * s, 8 * s);
+        for (uint32_t s = 0; s < 16; s++) xxh3_accumulate_stream(acc, in, 8 * s);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             uint64_t a = acc[i];
@@ -204,7 +225,7 @@ __device__ __forceinline__ uint64_t xxh3_record(const R &r, uint32_t n)
     }
     const uint32_t nstripes = ((n - 1) - (nblocks << 10)) >> 6;
 #pragma unroll 1
-    for (uint32_t s = 0; s < nstripes; s++) xxh3_accumulate<false>(acc, r, (nblocks << 10) + 64 * s, 8 * s);
+    for (uint32_t s = 0; s < nstripes; s++) xxh3_accumulate_stream(acc, in, 8 * s);
     xxh3_accumulate<true>(acc, r, n - 64, 121);
     uint64_t res = (uint64_t)n * XP64_1;
 #pragma unroll
