@@ -123,7 +123,11 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         // Kernels with parallelism inside a record pay off for multi-kilobyte records only: below the thresholds the
         // thread-per-record kernels win (length-sorted visiting order, 128-bit stream loads, shared-memory seed table).
         const bool long_ok = n && !(flags & (SHB_FLAG_FORCE_DIRECT | SHB_FLAG_NO_LONG_PATH));
-        const bool long_mode = long_ok && mean >= 4096;
+        // crossovers measured against the length-sorted direct kernels (tools/ab_direct.py, flags 0 vs 0x200):
+        // BLAKE3 chunk-parallel from ~10 kB mean (2-8 kB: direct x1.28; 8-24 kB: long x1.09; 10-50 kB: long x1.7),
+        // K12 leaf-parallel from ~48 kB (10-50 kB: direct x1.22; 50-100 kB: long x1.13; 100-200 kB: long x1.28)
+        const bool b3_long = long_ok && mean >= 10240;
+        const bool k12_long = long_ok && mean >= 49152;
         const size_t xxh3_warp_min = 12288;   // below: thread per record, stripes through 128-bit stream loads (x1.2-1.8)
         const size_t nt_warp_min = 2560;   // below: thread per record with the shared-memory seed table (x1.4-1.9)
         // Thread-per-record kernels can walk the records in descending length order (counting sort of the indices by
@@ -161,11 +165,11 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
                 CU(shb::launch_nthash_long(fused_upper, res, offs, n, slot_of[a], st));
             } else if (long_ok && a == SHB_XXH3 && mean >= xxh3_warp_min) {
                 CU(shb::launch_xxh3_long(fused_upper, res, offs, n, slot_of[a], st));
-            } else if (long_mode && mean >= 8192 && a == SHB_K12 && d_scratch) {
+            } else if (k12_long && a == SHB_K12 && d_scratch) {
                 ScratchLayout L(total_bytes, n);
                 CU(shb::launch_k12_long(fused_upper, res, offs, n, total_bytes, slot_of[a],
                                         static_cast<uint8_t *>(d_scratch) + L.b3_off, st));
-            } else if (long_mode && a == SHB_BLAKE3 && d_scratch) {
+            } else if (b3_long && a == SHB_BLAKE3 && d_scratch) {
                 ScratchLayout L(total_bytes, n);
                 CU(shb::launch_blake3_long(fused_upper, res, offs, n, total_bytes, slot_of[a],
                                            static_cast<uint8_t *>(d_scratch) + L.b3_off, st));

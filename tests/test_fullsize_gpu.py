@@ -73,6 +73,11 @@ def test_c4_long_reads(shb, oracle):
     _check(shb, oracle, 20_000, (10_000, 50_000), ["blake3", "nthash", "xxh3", "k12"], 0, 0xC4, shb.FLAG_NO_LONG_PATH)
 
 
+def test_very_long_reads_leaf_and_chunk_parallel_kernels(shb, oracle):
+    # mean 85 kB: above both crossovers (BLAKE3 chunk-parallel from 10 kB, K12 leaf-parallel from 48 kB mean)
+    _check(shb, oracle, 3_000, (50_000, 120_000), ["k12", "blake3", "xxh3", "nthash"], 1, 0xC6, shb.FLAG_NO_LONG_PATH, sample=300)
+
+
 def test_c5_variable_all_algorithms(shb, oracle):
     from seqhasher_b200.binding import ALGO_NAMES
     _check(shb, oracle, 300_000, (30, 3000), ALGO_NAMES, 3, 0xC5, shb.FLAG_NO_LENGTH_SORT, sample=3000)
