@@ -151,7 +151,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
             return 269u;                               // 1.05
         };
         const uint32_t *perm = nullptr;
-        if (d_scratch && n >= 1024 && (want & kSortMask) && !(flags & SHB_FLAG_NO_LENGTH_SORT)) {
+        if (d_scratch && n >= 1024 && n < ((size_t)1 << 32) && (want & kSortMask) && !(flags & SHB_FLAG_NO_LENGTH_SORT)) {   // 32-bit indices
             uint32_t lowest = 0xffffffffu;
             for (int a = 0; a < SHB_N_ALGOS; a++)
                 if ((want & kSortMask) >> a & 1u) lowest = std::min(lowest, min_waste_q8(a));
