@@ -169,7 +169,7 @@ struct SmemReader {
     }
     __device__ __forceinline__ uint32_t fin(uint32_t v) const
     {
-        if (DETECT) wsf |= (FMA_PREP ? fma_add(v, 0xdededfdfu) : v - 0x21212121u) & ~v;   // bit 7 of a byte <=> byte < 0x21
+        if (DETECT) wsf |= (FMA_PREP ? fma_add(v, 0xdedededfu) : v - 0x21212121u) & ~v;   // bit 7 of a byte <=> byte < 0x21
         return UPPER ? upper4<FMA_PREP>(v) : v;
     }
     __device__ __forceinline__ bool saw_ws_candidate() const { return DETECT && (wsf & 0x80808080u) != 0; }

@@ -210,6 +210,32 @@ def test_fused_strip_in_tile_path(shb, oracle):
             assert bad.size == 0, f"{a} flags={flags}: mismatch at records {bad[:8]}"
 
 
+@pytest.mark.parametrize("extra", [0, "direct"], ids=["tile", "direct"])
+def test_single_whitespace_byte_at_every_position(shb, oracle, extra):
+    """The speculative strip only looks again at records in which the readers SAW a byte < 0x21: one whitespace byte
+    of each kind, alone, at every offset (i.e. every byte lane of the 32-bit words, at every record alignment) must be
+    seen.  (A wrong SWAR constant once hid a lone 0x20 in byte lane 1.)"""
+    rng = np.random.default_rng(3)
+    recs = []
+    for ws in b" \t\n\x0b\x0c\r":
+        for L in (5, 8, 16, 17, 33, 64, 65, 130, 250):
+            for pos in range(min(L, 24)):
+                body = bytearray(rng.choice(np.frombuffer(b"ACGTacgtN", dtype=np.uint8), size=L).tobytes())
+                body[pos] = ws
+                recs.append(bytes(body))
+                body[L - 1 - pos % L] = ws          # a second one counted from the end
+                recs.append(bytes(body))
+    res, offs = csr_from_records(recs)
+    for flags in (2, 3):
+        f = flags | (shb.FLAG_FORCE_DIRECT if extra else 0)
+        want, wl = oracle.batch(res, offs, ALL, flags=flags, threads=8)
+        got, gl = shb.hash_batch(res, offs, ALL, flags=f)
+        assert (gl == wl).all(), f"lengths differ at records {np.nonzero(gl != wl)[0][:8]}"
+        for k, a in enumerate(ALL):
+            bad = np.nonzero((got[k] != want[k]).any(axis=1))[0]
+            assert bad.size == 0, f"{a} flags={flags}: mismatch at records {bad[:8]}"
+
+
 def test_hash_sharded_single_process(shb, oracle):
     # the in-process multi-device driver (one shb_batch per device); on a 1-GPU box this is one shard
     import torch
