@@ -189,3 +189,50 @@ def test_record_larger_than_chunk_grows_buffer(H, oracle):
     out = io.BytesIO()
     H.process_sequences_gpu(io.BytesIO(data), out, cfg, chunk_bytes=1 << 16, log=io.StringIO())
     assert out.getvalue() == expected(oracle, data, cfg)
+
+
+def _random_text(rng, fastq: bool) -> bytes:
+    eol = b"\r\n" if rng.random() < 0.25 else b"\n"
+    n = int(rng.integers(1, 400))
+    alpha = np.frombuffer(b"ACGTacgtNn" if rng.random() < 0.7 else b"ACGTacgtNnRYKM-*.", dtype=np.uint8)
+    out = [eol * int(rng.integers(0, 3))] if rng.random() < 0.3 else []
+    for i in range(n):
+        L = int(rng.choice([0, 1, 5, 59, 60, 61, 150, 700, 4100])) if rng.random() < 0.5 else int(rng.integers(0, 900))
+        if fastq:
+            L = max(L, 1)      # an empty FASTQ record is two blank lines: not a case the reference defines
+        seq = alpha[rng.integers(0, len(alpha), size=L)].tobytes()
+        name = b"r%d" % i + (b" some description; x=1" if rng.random() < 0.5 else b"") + (b" >not a record @either" if rng.random() < 0.1 else b"")
+        if fastq:
+            qual = bytes(rng.integers(33, 74, size=L).astype(np.uint8))
+            out.append(b"@" + name + eol + seq + eol + b"+" + (name if rng.random() < 0.2 else b"") + eol + qual + eol)
+        else:
+            wrap = int(rng.choice([0, 60, 70, 7]))
+            lines = [seq[k:k + wrap] for k in range(0, L, wrap)] if wrap and L else [seq]
+            if rng.random() < 0.1 and L > 4:
+                lines = [ln[:2] + b" " + ln[2:] for ln in lines]       # blanks inside sequence lines are stripped
+            body = eol.join(lines)
+            out.append(b">" + name + eol + body + eol + (eol if rng.random() < 0.05 else b""))
+    text = b"".join(out)
+    if rng.random() < 0.5:
+        text = text.rstrip(b"\r\n")                                      # last line without a line break
+    return text
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3] + [int(x) for x in os.environ.get("SHB_SOAK_SEEDS", "").split(",") if x])
+def test_random_text_soak(H, oracle, seed):
+    """Random FASTA / FASTQ text with the quirks bio's reader accepts (CRLF, wrapped and blank lines, blanks inside
+    sequence lines, '>' and '@' inside headers, empty sequences, missing final line break), random chunk sizes that
+    cut records anywhere, random configurations."""
+    rng = np.random.default_rng(seed)
+    algos = ["sha1", "md5", "xxh3", "xxhash", "murmur3", "nthash", "blake3", "rapidhash", "cityhash", "k12", "sha3", "rapidhash32"]
+    for it in range(14):
+        fastq = bool(rng.integers(2))
+        data = _random_text(rng, fastq)
+        kw = dict(hash_types=[algos[j] for j in rng.choice(12, size=int(rng.integers(1, 4)), replace=False)],
+                  headers_only=bool(rng.integers(2)), case_sensitive=bool(rng.integers(2)), no_file_name=bool(rng.integers(2)),
+                  input_file_name="in.fa")
+        cfg = H.Config(**kw)
+        chunk = int(rng.choice([12000, 20000, 70000, 1 << 20]))   # every record (<= 8.5 kB of text) fits
+        got = run_gpu(H, data, cfg, chunk=chunk)
+        want = expected(oracle, data, cfg)
+        assert got == want, (seed, it, fastq, kw, chunk, len(data))
