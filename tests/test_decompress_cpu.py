@@ -182,3 +182,39 @@ def test_truncated_inputs_fail_on_the_single_thread_paths_too():
         rc, out, err = zcat(blob[:len(blob) * 2 // 3], 1)
         assert rc == 1 and "EOF" in err, (blob[:4], err)
         assert data.startswith(out)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_gzip_random_streams_soak(seed):
+    """Random deflate streams: mixed content, random levels / strategies, random sync / full flushes in the middle
+    (empty stored blocks, window resets), several members, random worker counts and piece sizes."""
+    rng = np.random.default_rng(seed)
+    for it in range(12):
+        parts, blob = [], b""
+        for _member in range(int(rng.integers(1, 4))):
+            c = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, -15, int(rng.integers(5, 10)),
+                                 int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED])))
+            body, member = b"", b""
+            for _piece in range(int(rng.integers(1, 6))):
+                kind = rng.integers(4)
+                n = int(rng.integers(0, 400_000))
+                if kind == 0:
+                    chunk = DATA[int(rng.integers(0, 1_000_000)):][:n]
+                elif kind == 1:
+                    chunk = rng.bytes(n // 4)
+                elif kind == 2:
+                    chunk = bytes([int(rng.integers(32, 127))]) * n
+                else:
+                    chunk = (b"ACGT" * 50 + b"\n") * (n // 201)
+                member += chunk
+                body += c.compress(chunk)
+                if rng.random() < 0.5:
+                    body += c.flush(int(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH])))
+            body += c.flush()
+            blob += (b"\x1f\x8b\x08\0\0\0\0\0\0\x03" + body +
+                     struct.pack("<II", zlib.crc32(member) & 0xFFFFFFFF, len(member) & 0xFFFFFFFF))
+            parts.append(member)
+        want = b"".join(parts)
+        rc, out, err = zcat(blob, int(rng.choice([2, 3, 8])), int(rng.choice([8, 32, 128, 1024])))
+        assert rc == 0, (seed, it, err)
+        assert out == want, (seed, it, len(out), len(want))
