@@ -218,3 +218,26 @@ def test_gzip_random_streams_soak(seed):
         rc, out, err = zcat(blob, int(rng.choice([2, 3, 8])), int(rng.choice([8, 32, 128, 1024])))
         assert rc == 0, (seed, it, err)
         assert out == want, (seed, it, len(out), len(want))
+
+
+def test_bzip2_random_streams_soak():
+    """Random bzip2 inputs: several concatenated streams of random levels and content (runs that expand far beyond the
+    block size, incompressible bytes, text), random worker counts."""
+    rng = np.random.default_rng(5)
+    for it in range(8):
+        parts, blob = [], b""
+        for _stream in range(int(rng.integers(1, 5))):
+            kind, n = rng.integers(4), int(rng.integers(0, 1_500_000))
+            if kind == 0:
+                chunk = DATA[int(rng.integers(0, 1_000_000)):][:n]
+            elif kind == 1:
+                chunk = rng.bytes(n // 3)
+            elif kind == 2:
+                chunk = bytes([int(rng.integers(32, 127))]) * (n * 4)
+            else:
+                chunk = (b"ACGT" * 50 + b"\n") * (n // 201)
+            parts.append(chunk)
+            blob += bz2.compress(chunk, int(rng.integers(1, 10)))
+        rc, out, err = zcat(blob, int(rng.choice([2, 4, 8])))
+        assert rc == 0, (it, err)
+        assert out == b"".join(parts), (it, len(out))
