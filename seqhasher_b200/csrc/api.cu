@@ -174,7 +174,16 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
                 CU(shb::launch_blake3_long(fused_upper, res, offs, n, total_bytes, slot_of[a],
                                            static_cast<uint8_t *>(d_scratch) + L.b3_off, st));
             } else {
-                CU(shb::launch_hash_direct(a, fused_upper, res, offs, n, slot_of[a], (kSortMask >> a & 1u) ? perm : nullptr, st));
+                const uint32_t *order = (kSortMask >> a & 1u) ? perm : nullptr;
+                // Long records, where the global sort's scattered reads cost more than they save: every CTA sorts its own
+                // 128 consecutive records instead (kernels.cu: hash_direct_local_kernel).  Measured on 10-50 kB reads:
+                // sha1 x1.24, md5 x1.10, murmur3 x1.13 (x1.06-1.10 from 2 kB); xxhash, rapidhash, cityhash and xxh3 lose
+                // (x0.94 ... x0.6) and keep input order.
+                const bool local_ok = n >= 1024 && !(flags & SHB_FLAG_NO_LENGTH_SORT);
+                if (!order && local_ok &&
+                    (((a == SHB_SHA1 || a == SHB_MD5) && mean >= 16384) || (a == SHB_MURMUR3 && mean >= 4096)))
+                    order = shb::DIRECT_LOCAL_ORDER;
+                CU(shb::launch_hash_direct(a, fused_upper, res, offs, n, slot_of[a], order, st));
             }
         }
     }

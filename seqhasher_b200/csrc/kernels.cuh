@@ -25,7 +25,9 @@ constexpr uint32_t NORM_BLK = 4096;
 inline size_t norm_blocks(size_t total_bytes) { return total_bytes / NORM_BLK + 1; }
 
 // Direct path: one thread per record straight from global memory.
-// perm (may be null) = the order in which the records are visited, from launch_length_sort.
+// perm (may be null) = the order in which the records are visited, from launch_length_sort; DIRECT_LOCAL_ORDER =
+// every CTA sorts windows of 512 consecutive records by length itself (long records: keeps a warp's reads close).
+static const uint32_t *const DIRECT_LOCAL_ORDER = reinterpret_cast<const uint32_t *>(uintptr_t(1));
 cudaError_t launch_hash_direct(int algo, bool upper, const uint8_t *res, const int64_t *offs, size_t n,
                                uint8_t *out, const uint32_t *perm, cudaStream_t st);
 size_t length_sort_bytes(size_t n);
