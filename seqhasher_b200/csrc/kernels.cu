@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128) hash_direct_kernel(const uint8_t *__restr
 // to hashing multi-kilobyte records) and thread t takes rank t: each warp holds 32 records of similar length that
 // lie within the same few megabytes.  (A window of 512 with four records per thread was tried: it quarters the
 // number of records in flight and was 1.3-3x slower on 10-50 kB reads.)
-constexpr uint32_t LOCAL_WINDOW = 128;
+constexpr uint32_t LOCAL_WINDOW = 128;   // = threads per CTA: one record per thread
 template <int ALGO, bool UPPER>
 __global__ void __launch_bounds__(128) hash_direct_local_kernel(const uint8_t *__restrict__ res,
                                                                 const int64_t *__restrict__ offs, size_t n,
@@ -71,51 +71,40 @@ __global__ void __launch_bounds__(128) hash_direct_local_kernel(const uint8_t *_
     const size_t windows = (n + LOCAL_WINDOW - 1) / LOCAL_WINDOW;
     for (size_t w = blockIdx.x; w < windows; w += gridDim.x) {
         const size_t base = w * LOCAL_WINDOW;
-        uint32_t differs = 0, len0 = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < LOCAL_WINDOW / 128; j++) {
-            const uint32_t k = threadIdx.x + 128 * j;
-            const size_t i = base + k;
+        size_t i = base + threadIdx.x;
+        {
             const uint32_t len = i < n ? (uint32_t)(offs[i + 1] - offs[i]) : 0u;
-            if (j == 0) len0 = len;
-            differs |= len ^ len0;
-            s_key[k] = ((uint64_t)len << 32) | k;
-        }
-        differs |= len0 ^ __shfl_sync(0xffffffffu, len0, 0);
-        if (__syncthreads_or(differs != 0)) {   // equal lengths everywhere visible to a warp: keep input order
-            for (uint32_t size = 2; size <= LOCAL_WINDOW; size <<= 1)
-                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-                    for (uint32_t j = 0; j < (LOCAL_WINDOW + 255) / 256; j++) {
-                        const uint32_t p = threadIdx.x + 128 * j;                 // pair number
-                        if (p >= LOCAL_WINDOW / 2) break;
-                        const uint32_t lo = 2 * p - (p & (stride - 1));           // lower element of the pair
-                        const uint32_t hi = lo + stride;
-                        const bool descending = (lo & size) == 0;
-                        const uint64_t a = s_key[lo], b = s_key[hi];
-                        if ((a < b) == descending) { s_key[lo] = b; s_key[hi] = a; }
+            s_key[threadIdx.x] = ((uint64_t)len << 32) | threadIdx.x;
+            // equal lengths inside every warp: input order is already as good as it gets
+            if (__syncthreads_or(len != __shfl_sync(0xffffffffu, len, 0))) {
+                for (uint32_t size = 2; size <= LOCAL_WINDOW; size <<= 1)
+                    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                        if (threadIdx.x < LOCAL_WINDOW / 2) {
+                            const uint32_t p = threadIdx.x;                           // pair number
+                            const uint32_t lo = 2 * p - (p & (stride - 1));           // lower element of the pair
+                            const uint32_t hi = lo + stride;
+                            const bool descending = (lo & size) == 0;
+                            const uint64_t a = s_key[lo], b = s_key[hi];
+                            if ((a < b) == descending) { s_key[lo] = b; s_key[hi] = a; }
+                        }
+                        __syncthreads();
                     }
-                    __syncthreads();
-                }
+                i = base + (uint32_t)s_key[threadIdx.x];
+            }
         }
-#pragma unroll 1
-        for (uint32_t j = 0; j < LOCAL_WINDOW / 128; j++) {
-            const size_t i = base + (uint32_t)s_key[threadIdx.x + 128 * j];
-            if (i >= n) continue;
+        if (i < n) {
             const int64_t s = offs[i];
             const uint32_t len = (uint32_t)(offs[i + 1] - s);
             uint8_t *o = out + i * digest_size(ALGO);
             if (len == 0) {   // empty-sequence rule, seqhasher.go:292-295
                 zero_digest<ALGO>(o);
-                continue;
-            }
-            if (ALGO == A_NTHASH) {
+            } else if (ALGO == A_NTHASH) {
                 GlobalReader<UPPER> r(res, s);
                 store_be64(o, nthash_record_lut_stream<!UPPER>(r, len, s_nt));
-                continue;
+            } else {
+                GlobalReader<UPPER, true, (ALGO != A_K12 && ALGO != A_SHA1)> r(res, s);
+                hash_one<ALGO>(r, len, o);
             }
-            GlobalReader<UPPER, true, (ALGO != A_K12 && ALGO != A_SHA1)> r(res, s);
-            hash_one<ALGO>(r, len, o);
         }
         __syncthreads();   // the keys are rewritten for the next window
     }

@@ -14,7 +14,7 @@ st = torch.cuda.current_stream().cuda_stream
 SIZES = {0: 20, 1: 64, 2: 16, 3: 8, 4: 8, 5: 16, 6: 16, 7: 8, 8: 32, 9: 128, 10: 8}
 NAMES = {0: "sha1", 1: "sha3", 2: "md5", 3: "xxhash", 4: "xxh3", 5: "cityhash", 6: "murmur3", 7: "nthash", 8: "blake3", 9: "k12", 10: "rapidhash"}
 SHAPES = {"readme": (500_000, 30, 3000), "mid1k": (1_000_000, 800, 1200), "c4": (20_000, 10_000, 50_000),
-          "u500_1500": (700_000, 500, 1500), "u100_2000": (700_000, 100, 2000), "u900_2100": (500_000, 900, 2100), "fix1000": (700_000, 1000, 1000), "c4big": (150_000, 10_000, 50_000), "amp": (5_000_000, 100, 600), "amp250": (5_000_000, 200, 300), "fix250": (5_000_000, 250, 250), "u2k_8k": (300_000, 2000, 8000), "u5k_15k": (150_000, 5000, 15000), "u8k_24k": (100_000, 8000, 24000), "u50k_100k": (40_000, 50_000, 100_000), "u100k_200k": (20_000, 100_000, 200_000)}
+          "u500_1500": (700_000, 500, 1500), "u100_2000": (700_000, 100, 2000), "u900_2100": (500_000, 900, 2100), "fix1000": (700_000, 1000, 1000), "c4big": (150_000, 10_000, 50_000), "amp": (5_000_000, 100, 600), "amp250": (5_000_000, 200, 300), "fix250": (5_000_000, 250, 250), "u2k_8k": (300_000, 2000, 8000), "u5k_15k": (150_000, 5000, 15000), "u8k_24k": (100_000, 8000, 24000), "u50k_100k": (40_000, 50_000, 100_000), "fix5000": (200_000, 5000, 5000), "u100k_200k": (20_000, 100_000, 200_000)}
 only = sys.argv[1].split(",") if len(sys.argv) > 1 else list(SHAPES)
 algo_filter = sys.argv[2].split(",") if len(sys.argv) > 2 else [v for v in NAMES.values() if v not in ("xxh3", "nthash")]
 FLAGS = [int(x, 0) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]   # 0x200 = SHB_FLAG_NO_LONG_PATH
