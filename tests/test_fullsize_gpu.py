@@ -78,6 +78,12 @@ def test_very_long_reads_leaf_and_chunk_parallel_kernels(shb, oracle):
     _check(shb, oracle, 3_000, (50_000, 120_000), ["k12", "blake3", "xxh3", "nthash"], 1, 0xC6, shb.FLAG_NO_LONG_PATH, sample=300)
 
 
+def test_window_local_order_on_long_reads(shb, oracle):
+    # mean 25 kB, n >= 1024: sha1 / md5 / murmur3 run hash_direct_local_kernel (every CTA sorts its own 128 records);
+    # SHB_FLAG_NO_LENGTH_SORT is the plain input-order kernel
+    _check(shb, oracle, 4_000, (10_000, 40_000), ["sha1", "md5", "murmur3", "xxhash"], 1, 0xC7, shb.FLAG_NO_LENGTH_SORT, sample=400)
+
+
 def test_c5_variable_all_algorithms(shb, oracle):
     from seqhasher_b200.binding import ALGO_NAMES
     _check(shb, oracle, 300_000, (30, 3000), ALGO_NAMES, 3, 0xC5, shb.FLAG_NO_LENGTH_SORT, sample=3000)
