@@ -265,7 +265,8 @@ def main():
                  "frac_of_alu_pipe": (sha1_ach / probes["alu_pipe_lop3"]) if probes.get("alu_pipe_lop3") else None,
                  "probes_T": {k: (v / 1e12 if v else None) for k, v in probes.items()}, "theoretical_issue_T": theo / 1e12,
                  "work": f"{SHA1_INSTR_PER_BLOCK} int ops x {blocks_per_rec} blocks x {n} records per launch",
-                 "hbm_gbps": alg_bytes_sha1 / (ms_sha1 * 1e-3) / 1e9,
+                 "hbm_gbps": alg_bytes_sha1 / (ms_sha1 * 1e-3) / 1e9, "hbm_peak_gbps": hbm_peak,
+                 "hbm_frac": alg_bytes_sha1 / (ms_sha1 * 1e-3) / 1e9 / hbm_peak,   # far from the HBM roof: the kernel is integer-bound
                  "traffic": (2_580_202_000 + 197_736_960) if n == N_RECORDS else None,
                  "traffic_source": "ncu --set full, profiles/r01_sha1_tile.summary.txt: dram read 2.580 GB + write 0.198 GB per launch "
                                    "(algorithmic: %.3f GB)" % (alg_bytes_sha1 / 1e9),
