@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--big", action="store_true", help="tens of thousands of records per batch (many CTAs in every sort / scan)")
     a = ap.parse_args()
     B.init(1)
     O.build()
@@ -27,16 +28,16 @@ def main():
     bad = 0
     for it in range(a.iters):
         dist = dists[rng.integers(len(dists))]
-        n = int(rng.choice([1, 2, 31, 127, 128, 129, 1000, 1500, 3000, 6000]))
+        n = int(rng.choice([20_000, 50_000, 130_000])) if a.big else int(rng.choice([1, 2, 31, 127, 128, 129, 1000, 1500, 3000, 6000]))
         if dist == "fixed":
             lens = np.full(n, int(rng.choice([1, 63, 64, 150, 250, 1000, 5000])))
         elif dist == "narrow":
             base = int(rng.choice([100, 800, 3000]))
             lens = rng.integers(base, base + base // 4 + 1, size=n)
         elif dist == "wide":
-            lens = rng.integers(1, int(rng.choice([600, 3000, 20000])), size=n)
+            lens = rng.integers(1, int(rng.choice([600, 3000] if a.big else [600, 3000, 20000])), size=n)
         elif dist == "bimodal":
-            lens = np.where(rng.random(n) < 0.5, rng.integers(20, 60, size=n), rng.integers(2000, 9000, size=n))
+            lens = np.where(rng.random(n) < 0.5, rng.integers(20, 60, size=n), rng.integers(2000, 3000 if a.big else 9000, size=n))
         elif dist == "long":
             n = min(n, 300)
             lens = rng.integers(8000, int(rng.choice([30000, 120000])), size=n)
