@@ -50,8 +50,12 @@ inline long gzip_header_len(const uint8_t *p, size_t n)
             if (q >= n) return 0;
             q++;
         }
-    if (flg & 2) q += 2;
-    if (q > n) return 0;
+    if (flg & 2) {   // FHCRC: CRC-16 of the header so far (gzip.Reader checks it too)
+        if (q + 2 > n) return 0;
+        const uint32_t want = p[q] | (p[q + 1] << 8);
+        if ((crc32(crc32(0L, Z_NULL, 0), p, (uInt)q) & 0xffffu) != want) return -1;
+        q += 2;
+    }
     return (long)q;
 }
 

@@ -108,6 +108,10 @@ def test_gzip_errors_like_the_reference_reader():
     assert rc == 1 and "invalid checksum" in err
     rc, _, err = zcat(blob + b"\0" * 512, 4, 64)
     assert rc == 1 and "invalid header" in err
+    hdr = bytearray(gz(DATA[:100_000], 6, flags=2, name=b"f.fa"))
+    hdr[12] ^= 0x01                                            # inside FNAME: the header CRC-16 no longer matches
+    rc, _, err = zcat(bytes(hdr), 4, 64)
+    assert rc == 1 and "invalid header" in err
     bad = bytearray(blob)
     bad[300_000] ^= 0xFF
     rc, _, err = zcat(bytes(bad), 4, 64)
