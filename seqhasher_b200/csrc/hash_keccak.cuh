@@ -182,19 +182,25 @@ __device__ __forceinline__ void kt128_leaf_cv(const R &r, uint32_t len, uint32_t
     for (int j = 0; j < 4; j++) cv[j] = a[j];
 }
 
-// final node; leaf CVs come from `leaf(c, cv)` (computed inline, or read back from the leaf kernel's output)
-template <class R, class LeafFn>
-__device__ __forceinline__ void kt128_final_node(const R &r, uint32_t len, uint8_t *out, LeafFn leaf)
+// The final node in two steps.  Step 1, the 48 full rate blocks of S_0 (8064 of its 8192 bytes), depends on the
+// record alone — it is 8 KiB of serial sponge per record and can run beside the leaves; step 2 takes that state, the
+// last 128 bytes of S_0, the leaf CVs and the trailer.
+template <class R>
+__device__ __forceinline__ void kt128_s0_state(const R &r, uint64_t (&f)[25])
 {
-    uint64_t f[25];
 #pragma unroll
     for (int i = 0; i < 25; i++) f[i] = 0;
-    // S_0: 8192 bytes = 48 full rate blocks + 16 lanes
     for (uint32_t blk = 0; blk < 48; blk++) {
 #pragma unroll
         for (int i = 0; i < 21; i++) f[i] ^= r.u64(blk * 168 + 8 * i);
         keccak_p<12>(f);
     }
+}
+
+// step 2; leaf CVs come from `leaf(c, cv)` (computed inline, or read back from the leaf kernel's output)
+template <class R, class LeafFn>
+__device__ __forceinline__ void kt128_final_from_state(const R &r, uint32_t len, uint8_t *out, uint64_t (&f)[25], LeafFn leaf)
+{
     uint64_t pend[21];
 #pragma unroll
     for (int i = 0; i < 16; i++) pend[i] = r.u64(48 * 168 + 8 * i);
@@ -239,6 +245,14 @@ __device__ __forceinline__ void kt128_final_node(const R &r, uint32_t len, uint8
     uint64_t *o = reinterpret_cast<uint64_t *>(out);
 #pragma unroll
     for (int i = 0; i < 16; i++) o[i] = f[i];
+}
+
+template <class R, class LeafFn>
+__device__ __forceinline__ void kt128_final_node(const R &r, uint32_t len, uint8_t *out, LeafFn leaf)
+{
+    uint64_t f[25];
+    kt128_s0_state(r, f);
+    kt128_final_from_state(r, len, out, f, leaf);
 }
 
 template <class R>

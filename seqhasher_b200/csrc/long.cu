@@ -230,14 +230,29 @@ __global__ void k12_count_leaves_kernel(const int64_t *__restrict__ offs, size_t
     }
 }
 
-// One thread per leaf over the flattened leaf list of the batch: CV (32 bytes) to cvs[global leaf id].
+// One thread per leaf over the flattened leaf list of the batch: CV (32 bytes) to cvs[global leaf id].  Threads
+// from s0_first on take one record each and run the record-only part of its final node (the 48 full rate blocks of
+// S_0) into s0[record][25]: those 8 KiB per record would otherwise be serial work of the final kernel.
 template <bool UPPER>
 __global__ void __launch_bounds__(128) k12_leaves_kernel(const uint8_t *__restrict__ res, const int64_t *__restrict__ offs,
                                                          size_t n, const int64_t *__restrict__ leaf_base,
-                                                         uint64_t *__restrict__ cvs)
+                                                         uint64_t *__restrict__ cvs, int64_t s0_first, uint64_t *__restrict__ s0)
 {
     const int64_t total = leaf_base[n];
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= s0_first) {
+        const size_t i = (size_t)(g - s0_first);
+        if (i >= n) return;
+        const int64_t s = offs[i];
+        if (offs[i + 1] - s < 8192) return;
+        GlobalReader<UPPER, true, false> r(res, s);
+        uint64_t f[25];
+        kt128_s0_state(r, f);
+        uint64_t *dst = s0 + i * 25;
+#pragma unroll
+        for (int k = 0; k < 25; k++) dst[k] = f[k];
+        return;
+    }
     if (g >= total) return;
     size_t lo = 0, hi = n;
     while (hi - lo > 1) {
@@ -261,7 +276,8 @@ __global__ void __launch_bounds__(128) k12_leaves_kernel(const uint8_t *__restri
 template <bool UPPER>
 __global__ void __launch_bounds__(128) k12_final_kernel(const uint8_t *__restrict__ res, const int64_t *__restrict__ offs,
                                                         size_t n, const int64_t *__restrict__ leaf_base,
-                                                        const uint64_t *__restrict__ cvs, uint8_t *__restrict__ out)
+                                                        const uint64_t *__restrict__ cvs, const uint64_t *__restrict__ s0,
+                                                        uint8_t *__restrict__ out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -278,7 +294,10 @@ __global__ void __launch_bounds__(128) k12_final_kernel(const uint8_t *__restric
         return;
     }
     const uint64_t *my = cvs + leaf_base[i] * 4;
-    kt128_final_node(r, len, o, [&](uint32_t c, uint64_t (&cv)[4]) {
+    uint64_t f[25];
+#pragma unroll
+    for (int k = 0; k < 25; k++) f[k] = s0[i * 25 + k];
+    kt128_final_from_state(r, len, o, f, [&](uint32_t c, uint64_t (&cv)[4]) {
         const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(my + (size_t)(c - 1) * 4));
         const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(my + (size_t)(c - 1) * 4 + 2));
         cv[0] = a.x; cv[1] = a.y; cv[2] = b.x; cv[3] = b.y;
@@ -302,13 +321,18 @@ cudaError_t launch_k12_long(bool upper, const uint8_t *res, const int64_t *offs,
     cudaError_t e = scan_counts(counts, n, leaf_base, scan_tmp, st);
     if (e != cudaSuccess) return e;
     const size_t max_leaves = total_bytes / 8192 + 1;
-    const unsigned blocks = (unsigned)((max_leaves + 127) / 128);
+    const unsigned leaf_blocks = (unsigned)((max_leaves + 127) / 128);
+    const int64_t s0_first = (int64_t)leaf_blocks * 128;
+    const unsigned blocks = leaf_blocks + (unsigned)((n + 127) / 128);
+    // S_0 states (25 lanes per record) behind the CVs inside the region sized for BLAKE3's 32 bytes per KiB
+    uint64_t *s0 = cvs + up(max_leaves * 32) / 8;
+    if (up(max_leaves * 32) + n * 200 > up(max_chunks0 * 32)) return cudaErrorInvalidValue;   // callers pass mean >= 8 KiB
     if (upper) {
-        k12_leaves_kernel<true><<<blocks, 128, 0, st>>>(res, offs, n, leaf_base, cvs);
-        k12_final_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(res, offs, n, leaf_base, cvs, out);
+        k12_leaves_kernel<true><<<blocks, 128, 0, st>>>(res, offs, n, leaf_base, cvs, s0_first, s0);
+        k12_final_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(res, offs, n, leaf_base, cvs, s0, out);
     } else {
-        k12_leaves_kernel<false><<<blocks, 128, 0, st>>>(res, offs, n, leaf_base, cvs);
-        k12_final_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(res, offs, n, leaf_base, cvs, out);
+        k12_leaves_kernel<false><<<blocks, 128, 0, st>>>(res, offs, n, leaf_base, cvs, s0_first, s0);
+        k12_final_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(res, offs, n, leaf_base, cvs, s0, out);
     }
     g_launches += 2;
     return cudaGetLastError();
