@@ -16,6 +16,8 @@ namespace shb {
 // ALU pipe.  The multipliers come from kernel parameters (values the compiler cannot see), otherwise
 // ptxas folds the products back into shifts.  VARIANT bits choose what moves to the FMA pipe:
 //   1: rol(b,30)   2: the schedule's rol(.,1)   4: rol(a,5) as two separate addends   8: W[t]+K
+//   16 / 32: rol(b,30) / the schedule's rol as IMAD.HI + IMAD (no IMAD.WIDE) — also slower than SHF:
+//   23.6 T (variant 8) against 21.0 / 21.3 / 18.2 T (variants 24 / 40 / 56), tools/probe_sha1_variants.py
 struct PipeConsts {
     uint32_t one, p1, p5, p30;   // 1, 2, 32, 1<<30
 };
@@ -25,6 +27,11 @@ __device__ __forceinline__ uint32_t fma_rol(uint32_t x, uint32_t pow2, uint32_t 
 {
     uint64_t p = (uint64_t)x * (uint64_t)pow2;
     return (uint32_t)(p >> 32) * one + (uint32_t)p;
+}
+// the same rotate as IMAD.HI + IMAD (variant bits 16 / 32): no 64-bit register pair, no IMAD.WIDE
+__device__ __forceinline__ uint32_t fma_rol_hi(uint32_t x, uint32_t pow2)
+{
+    return x * pow2 + __umulhi(x, pow2);
 }
 
 template <int VARIANT>
@@ -38,7 +45,7 @@ __device__ __forceinline__ void sha1_compress_v(uint32_t (&h)[5], uint32_t (&w)[
             wt = w[t];
         } else {
             uint32_t x = w[(t - 3) & 15] ^ w[(t - 8) & 15] ^ w[(t - 14) & 15] ^ w[t & 15];
-            wt = (VARIANT & 2) ? fma_rol(x, pc.p1, pc.one) : rotl32(x, 1);
+            wt = (VARIANT & 32) ? fma_rol_hi(x, pc.p1) : (VARIANT & 2) ? fma_rol(x, pc.p1, pc.one) : rotl32(x, 1);
             w[t & 15] = wt;
         }
         uint32_t f, k;
@@ -55,7 +62,7 @@ __device__ __forceinline__ void sha1_compress_v(uint32_t (&h)[5], uint32_t (&w)[
             tmp = rotl32(a, 5) + f + e + kw;
         }
         e = d; d = c;
-        c = (VARIANT & 1) ? fma_rol(b, pc.p30, pc.one) : rotl32(b, 30);
+        c = (VARIANT & 16) ? fma_rol_hi(b, pc.p30) : (VARIANT & 1) ? fma_rol(b, pc.p30, pc.one) : rotl32(b, 30);
         b = a; a = tmp;
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;

@@ -700,6 +700,9 @@ cudaError_t launch_probe(int kind, int iters, uint32_t *sink, double *lane_instr
     case 29: launch_probe_sha1<13>(iters, sink, st); break;
     case 30: launch_probe_sha1<14>(iters, sink, st); break;
     case 31: launch_probe_sha1<15>(iters, sink, st); break;
+    case 40: launch_probe_sha1<24>(iters, sink, st); break;   // 8 + rol30 as IMAD.HI
+    case 56: launch_probe_sha1<40>(iters, sink, st); break;   // 8 + schedule rol1 as IMAD.HI
+    case 72: launch_probe_sha1<56>(iters, sink, st); break;   // 8 + both
     default: return cudaErrorInvalidValue;
     }
     g_launches++;

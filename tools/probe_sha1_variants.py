@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 from seqhasher_b200 import binding as B
 B.init(1)
 ref = None
-for v in range(16):
+for v in list(range(16)) + [24, 40, 56]:
     r = B.probe_int_peak(16 + v, 2000)
     c = B.probe_last_checksum()
     ref = c if ref is None else ref
