@@ -1,5 +1,10 @@
-"""A/B of the direct (thread-per-record, global-memory) path on mid and long records.
-SHB_LIB selects the library; prints ms per pass and residue GB/s per (shape, algorithm, flags).
+"""A/B of the hash kernels on chosen length distributions (SHB_LIB selects the library build, so two builds can be
+compared in one gpurun call).  Prints ms per pass, residue GB/s and a digest checksum per (shape, algorithm, flags).
+usage: python tools/ab_direct.py [shapes] [algorithms] [flags]
+  shapes      comma list of SHAPES keys (default: all)          e.g. readme,mid1k,c4big
+  algorithms  comma list of names (default: all but xxh3/nthash) e.g. sha1,md5,xxh3
+  flags       comma list of SHB_FLAG_* values (default 0,1)      e.g. 1,3  or  0,0x200 (0x200 = no long-record kernels,
+              0x100 = force the direct path, 0x400 = no length sort)
 Standalone ctypes loader so that older builds of the library can be compared."""
 import ctypes, os, sys, torch
 c = ctypes
