@@ -56,6 +56,11 @@ enum shb_algo {
 #define SHB_ERR_CUDA (-4)        /* a CUDA call failed; see shb_last_error() */
 #define SHB_ERR_OFFSETS (-5)     /* offsets not monotone / record longer than 2^31-1 bytes */
 #define SHB_ERR_FORMAT (-6)      /* text is not FASTA/FASTQ ("fastx: invalid FASTA/Q format") */
+/* shb_textproc_run only (> 0, not a failure of the call): the text at shb_textproc_consumed() is not a valid record
+ * (bad FASTQ '@' / '+' marker, input ending inside a FASTQ record).  The output holds the records before it — the
+ * reference's reader yields those before it fails (seqhasher.go:228-239) — and the host then reports
+ * "Error reading record: fastx: invalid FASTA/Q format". */
+#define SHB_PARTIAL_FORMAT 1
 
 /* Library lifetime.  n_gpus <= 0 uses every visible device; devices 0..n-1 otherwise.  Returns the
  * number of devices in use (>0) or an error.  Idempotent. */
@@ -134,7 +139,9 @@ unsigned long long shb_launch_count(void);
  * (the host skips leading blank lines and sniffs the format from the first byte: '>' FASTA, '@' FASTQ, else
  * the reference's "fastx: invalid FASTA/Q format" error); call shb_textproc_run (blocking); write
  * shb_textproc_output() to the sink; move the unconsumed tail (input + shb_textproc_consumed()) to the front
- * and refill.  is_final = this chunk ends the input (a missing last line break is added).  label = the file
+ * and refill; a chunk with more records than the index holds (capacity / 16 + 1024) is consumed only up to that many,
+ * so also after the final chunk the host runs the unconsumed tail again until nothing is left.  is_final = this chunk
+ * ends the input (a missing last line break is added).  label = the file
  * name field (cfg.inputFileName or --name), NULL for --nofilename / stdin.  flags: SHB_FLAG_UPPER only (the
  * splitter always strips).  shb_textproc_empty_records() = records with an empty sequence, for which the
  * reference logs one line per hash type (seqhasher.go:293). */

@@ -5,7 +5,9 @@
  * object and the `--impl reference` arm; a standalone process is used because OpenMP teams created inside the
  * Python interpreter of this image stay on one CPU.
  *
- * usage: cpu_bench <n_records> <read_len> <seed> <lower_permille> <flags> <threads> <accel> <steps> <algo>[,<algo>..]
+ * usage: cpu_bench <n_records> <read_len | lo-hi> <seed> <lower_permille> <flags> <threads> <accel> <steps> <algo>[,<algo>..] [n_permille]
+ * read_len "lo-hi": record i has length lo + ((splitmix64((seed ^ LEN_SALT) + i * GOLDEN) >> 32) * (hi - lo + 1) >> 32)
+ * (bench.py builds the same offsets with numpy).  n_permille of the bases become 'N' (config C4).
  * prints one JSON line: seqs/s (best step), per-step ms, and a 64-bit XOR-fold checksum of every digest.
  */
 #define _GNU_SOURCE
@@ -37,7 +39,11 @@ int main(int argc, char **argv)
         fprintf(stderr, "usage: %s n len seed lower_permille flags threads accel steps algos\n", argv[0]);
         return 2;
     }
-    const size_t n = strtoull(argv[1], NULL, 10), L = strtoull(argv[2], NULL, 10);
+    const size_t n = strtoull(argv[1], NULL, 10);
+    char *dash = NULL;
+    const size_t L = strtoull(argv[2], &dash, 10);
+    const size_t Lhi = (dash && *dash == '-') ? strtoull(dash + 1, NULL, 10) : L;
+    const unsigned n_permille = argc > 10 ? (unsigned)atoi(argv[10]) : 0;
     const uint64_t seed = strtoull(argv[3], NULL, 0);
     const unsigned lower = (unsigned)atoi(argv[4]);
     const int flags = atoi(argv[5]), threads = atoi(argv[6]), accel = atoi(argv[7]), steps = atoi(argv[8]);
@@ -48,18 +54,28 @@ int main(int argc, char **argv)
         if (id < 0) { fprintf(stderr, "unknown algo %s\n", tok); return 2; }
         algos[n_algos++] = id;
     }
-    const size_t total = n * L;
-    uint8_t *res = (uint8_t *)malloc(total + 64);
     int64_t *offs = (int64_t *)malloc((n + 1) * sizeof(int64_t));
-    if (!res || !offs) return 3;
+    if (!offs) return 3;
+    offs[0] = 0;
+    for (size_t i = 0; i < n; i++) {
+        size_t len = L;
+        if (Lhi > L) {
+            const uint64_t z = splitmix64((seed ^ 0x6c656e67746873ULL) + (uint64_t)i * 0x9E3779B97F4A7C15ULL);
+            len = L + (size_t)(((z >> 32) * (uint64_t)(Lhi - L + 1)) >> 32);
+        }
+        offs[i + 1] = offs[i] + (int64_t)len;
+    }
+    const size_t total = (size_t)offs[n];
+    uint8_t *res = (uint8_t *)malloc(total + 64);
+    if (!res) return 3;
 #pragma omp parallel for schedule(static)
     for (long long j = 0; j < (long long)total; j++) {
         const uint64_t z = splitmix64(seed + (uint64_t)j * 0x9E3779B97F4A7C15ULL);
         uint8_t c = (uint8_t)"ACGT"[z & 3];
+        if ((((z >> 32) & 0xFFFFF) * 1000 >> 20) < n_permille) c = 'N';
         if ((((z >> 8) & 0xFFFFF) * 1000 >> 20) < lower) c |= 0x20;
         res[j] = c;
     }
-    for (size_t i = 0; i <= n; i++) offs[i] = (int64_t)(i * L);
     uint8_t *dig[SHO_N_ALGOS];
     for (int k = 0; k < n_algos; k++) dig[k] = (uint8_t *)malloc(n * sho_digest_size(algos[k]) + 8);
     double best = 1e30, sum = 0;
@@ -75,9 +91,9 @@ int main(int argc, char **argv)
         for (size_t i = 0; i + 8 <= bytes; i += 8) { uint64_t v; memcpy(&v, dig[k] + i, 8); chk ^= v; }
         for (size_t i = bytes & ~(size_t)7; i < bytes; i++) chk ^= (uint64_t)dig[k][i] << (8 * (i & 7));
     }
-    printf("{\"records\": %zu, \"read_len\": %zu, \"threads\": %d, \"accel\": %d, \"accel_available\": %d, \"steps\": %d, "
+    printf("{\"records\": %zu, \"read_len\": %zu, \"read_len_hi\": %zu, \"residue_bytes\": %zu, \"threads\": %d, \"accel\": %d, \"accel_available\": %d, \"steps\": %d, "
            "\"ms_per_step\": %.3f, \"best_ms\": %.3f, \"seqs_per_s\": %.1f, \"checksum\": \"%016llx\"}\n",
-           n, L, threads, accel ? sho_accel_available() : 0, sho_accel_available(), steps, sum / steps * 1e3, best * 1e3,
+           n, L, Lhi, total, threads, accel ? sho_accel_available() : 0, sho_accel_available(), steps, sum / steps * 1e3, best * 1e3,
            n / (sum / steps), (unsigned long long)chk);
     return 0;
 }

@@ -34,6 +34,7 @@ EXPORTS = [
     "shb_textproc_input", "shb_textproc_capacity", "shb_textproc_run", "shb_textproc_output", "shb_textproc_consumed",
     "shb_textproc_records", "shb_textproc_empty_records", "shb_textproc_last_ms",
 ]
+PARTIAL_FORMAT = 1   # shb_textproc_run: SHB_PARTIAL_FORMAT
 FORMAT_FASTA = 1
 FORMAT_FASTQ = 2
 
@@ -275,8 +276,10 @@ class TextProc:
         L = lib()
         ids = list(algos)
         arr = (ctypes.c_int * max(len(ids), 1))(*ids)
-        _check(L.shb_textproc_run(self._h, n_bytes, fmt, 1 if is_final else 0, arr, len(ids), flags,
-                                  1 if headers_only else 0, label), "shb_textproc_run")
+        rc = L.shb_textproc_run(self._h, n_bytes, fmt, 1 if is_final else 0, arr, len(ids), flags,
+                                1 if headers_only else 0, label)
+        _check(rc, "shb_textproc_run")
+        self.partial_format = rc == PARTIAL_FORMAT   # the text at `consumed` is malformed; the output holds what precedes it
         nb = ctypes.c_size_t(0)
         p = L.shb_textproc_output(self._h, ctypes.byref(nb))
         # zero-copy view of the pinned output buffer (valid until the next run)

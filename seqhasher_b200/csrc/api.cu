@@ -561,7 +561,7 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
 {
     if (!t) return fail(SHB_ERR_BAD_ARG, "null textproc");
     if (int rc = check_algos(algos, n_algos)) return rc;
-    if (n_algos > SHB_N_ALGOS * 4) return fail(SHB_ERR_BAD_ARG, "too many hash types");
+    if (n_algos > shb::FMT_MAX_FIELDS) return fail(SHB_ERR_BAD_ARG, "too many hash types (at most 48 fields per record)");
     if (n_bytes > t->cap) return fail(SHB_ERR_CAPACITY, "text larger than the textproc capacity");
     if (format != SHB_FORMAT_FASTA && format != SHB_FORMAT_FASTQ) return fail(SHB_ERR_BAD_ARG, "format must be FASTA or FASTQ");
     const size_t label_len = label ? std::strlen(label) : 0;
@@ -582,12 +582,15 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
     CU(cudaMemcpyAsync(t->h_info, t->d_info, sizeof(shb::FxInfo), cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(t->ev[2], st));
     CU(cudaStreamSynchronize(st));
-    if (t->h_info->status == shb::FX_BAD_MARKER) return fail(SHB_ERR_FORMAT, "fastx: invalid FASTA/Q format");
-    if (t->h_info->status == shb::FX_TOO_MANY_RECORDS) return fail(SHB_ERR_CAPACITY, "more records than the textproc can index; use smaller chunks");
+    // FX_BAD_MARKER: the records before the malformed one are still hashed and formatted (the reference's reader yields
+    // them before it fails); FX_MORE: the record index was full, the caller resumes at `consumed`.
+    const bool malformed = t->h_info->status == shb::FX_BAD_MARKER;
+    const int done_rc = malformed ? SHB_PARTIAL_FORMAT : SHB_OK;
+    if (malformed) t_err = "fastx: invalid FASTA/Q format";
     const size_t n = (size_t)t->h_info->n_records, total = (size_t)t->h_info->n_residues;
     t->n_records = n;
     t->consumed = (size_t)t->h_info->consumed;
-    if (n == 0) return SHB_OK;
+    if (n == 0) return done_rc;
     // 2. hash (the residues are already whitespace-free; upper-casing is fused into the hash kernels)
     std::vector<size_t> slot_off(n_algos + 1, 0);
     for (int k = 0; k < n_algos; k++) slot_off[k + 1] = slot_off[k] + align_up(n * shb::digest_size(algos[k]), 256);
@@ -614,8 +617,7 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
     shb::FmtCfg cfg{};
     cfg.label = t->d_label;
     cfg.label_len = label ? (int)label_len : -1;
-    cfg.n_algos = n_algos > SHB_N_ALGOS ? SHB_N_ALGOS : n_algos;
-    if (n_algos > SHB_N_ALGOS) return fail(SHB_ERR_BAD_ARG, "at most 12 hash fields per record in the GPU formatter");
+    cfg.n_algos = n_algos;
     for (int k = 0; k < n_algos; k++) { cfg.dsize[k] = shb::digest_size(algos[k]); cfg.digests[k] = d_slots[k]; }
     cfg.headers_only = headers_only;
     cfg.fastq = format == SHB_FORMAT_FASTQ;
@@ -641,7 +643,7 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
     CU(cudaStreamSynchronize(st));
     for (int k = 0; k < 5; k++) cudaEventElapsedTime(&t->ms[k], t->ev[k], t->ev[k + 1]);
     t->out_bytes = out_bytes;
-    return SHB_OK;
+    return done_rc;
 }
 
 const uint8_t *shb_textproc_output(shb_textproc *t, size_t *out_bytes)

@@ -308,12 +308,16 @@ inline unsigned decomp_threads()
 
 // Sniff the magic bytes and wrap the file in the matching decompressor; compressed inputs are decoded on a
 // read-ahead thread so that they overlap the consumer.
-inline std::unique_ptr<Source> open_maybe_compressed(FILE *f, bool own)
+inline std::unique_ptr<Source> open_maybe_compressed(FILE *f, bool own, bool *compressed = nullptr)
 {
     auto fs = std::make_unique<FileSource>(f, own);
     uint8_t head[6];
     size_t k = fread(head, 1, sizeof head, f);
     fs->unread(head, k);
+    if (compressed)
+        *compressed = (k >= 2 && head[0] == 0x1f && head[1] == 0x8b) || (k >= 3 && head[0] == 'B' && head[1] == 'Z' && head[2] == 'h') ||
+                      (k >= 6 && memcmp(head, "\xfd" "7zXZ\0", 6) == 0) ||
+                      (k >= 4 && head[0] == 0x28 && head[1] == 0xb5 && head[2] == 0x2f && head[3] == 0xfd);
     const unsigned threads = decomp_threads();
     if (k >= 2 && head[0] == 0x1f && head[1] == 0x8b) {
         if (threads >= 2) {

@@ -3,12 +3,20 @@
 // and decompression; everything inside processSequences' record loop (seqhasher.go:227-283) runs on the GPU
 // through shb_textproc.  Go's `flag` rules are reproduced: -x and --x alike, `-x=v` or `-x v`, parsing stops
 // at the first positional ("-" included) or after "--".
+#include <atomic>
+#include <cerrno>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <sys/stat.h>
 
 #include "../../../include/seqhash_b200.h"
 #include "decompress.hpp"
@@ -135,36 +143,223 @@ ParseResult parse_flags(int argc, char **argv, Config &cfg, std::string &err)
 
 bool is_blank(uint8_t c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
+// Where the last record of buf[0, n) starts, so that buf[0, cut) holds complete records only (0: no such place).
+// FASTA: the last line-initial '>' (the splitter's own definition of a record start).  FASTQ: the last line that
+// starts with '@' and whose next-but-one line starts with '+' — a quality line may start with '@' too, but then
+// the line two below it is a sequence line, which never starts with '+'.
+size_t find_cut(const uint8_t *buf, size_t n, int format)
+{
+    if (format == SHB_FORMAT_FASTA) {
+        size_t hi = n;
+        while (hi > 1) {
+            const void *q = memrchr(buf + 1, '>', hi - 1);
+            if (!q) return 0;
+            const size_t p = (size_t)((const uint8_t *)q - buf);
+            if (buf[p - 1] == '\n') return p;
+            hi = p;
+        }
+        return 0;
+    }
+    size_t l1 = 0, l2 = 0;   // starts of the two lines below the candidate (0 = not seen yet)
+    size_t hi = n;
+    while (hi > 0) {
+        const void *q = hi > 1 ? memrchr(buf, '\n', hi - 1) : nullptr;   // the line break that ends the previous line
+        const size_t ls = q ? (size_t)((const uint8_t *)q - buf) + 1 : 0;
+        if (ls == 0) return 0;
+        if (ls < n && l2 && buf[ls] == '@' && buf[l2] == '+') return ls;
+        l2 = l1;
+        l1 = ls;
+        hi = ls;   // continue before this line's start (hi - 1 is the '\n' just found)
+    }
+    return 0;
+}
+
+// One chunk slot = one shb_textproc (pinned text buffer, device buffers, stream) + the host thread that runs it.
+// Chunks are dealt to the slots round-robin (slot = seq % K, K = 2 per GPU) and written in chunk order, so the
+// copy to the device, the kernels and the copy back of one chunk overlap the reading of the next and the writing
+// of the previous one, on as many GPUs as were selected (seqhasher.go:227-283 is one sequential loop).
+struct Slot {
+    int device = 0;
+    shb_textproc *tp = nullptr;
+    size_t cap = 0;
+    uint8_t *buf = nullptr;
+    // the job (written by the reader before `ready` is raised)
+    size_t n_bytes = 0;
+    bool is_final = false;
+    bool whole = false;      // the chunk holds complete records only: run it to the end, however many passes
+    // the result (written by the worker before `done` is raised)
+    int rc = 0;
+    std::string err;
+    std::vector<uint8_t> acc;   // output of all passes but the last
+    size_t consumed = 0, n_empty = 0;
+    long long ready = -1, done = -1, freed = -1;   // chunk sequence numbers
+    bool quit = false;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::thread worker;
+};
+
+struct RunArgs {
+    int format = 0;
+    std::vector<int> ids;
+    unsigned flags = 0;
+    int headers_only = 0;
+    const char *label = nullptr;
+};
+
+void slot_worker(Slot *s, const RunArgs *a)
+{
+    long long seq = -1;
+    while (true) {
+        {
+            std::unique_lock<std::mutex> lk(s->mu);
+            s->cv.wait(lk, [&] { return s->quit || s->ready > seq; });
+            if (s->ready <= seq) return;
+            seq = s->ready;
+        }
+        s->acc.clear();
+        s->n_empty = 0;
+        s->err.clear();
+        size_t off = 0, n = s->n_bytes;
+        int rc = 0;
+        while (true) {
+            rc = shb_textproc_run(s->tp, n, a->format, s->is_final ? 1 : 0, a->ids.empty() ? nullptr : a->ids.data(),
+                                  (int)a->ids.size(), a->flags, a->headers_only, a->label);
+            if (rc < 0) { s->err = shb_last_error(); break; }
+            s->n_empty += shb_textproc_empty_records(s->tp);
+            const size_t used = shb_textproc_consumed(s->tp);
+            off += used;
+            // more records than the index holds: the rest of a whole chunk goes through again
+            if (rc != 0 || !s->whole || used == 0 || used >= n) break;
+            size_t nout = 0;
+            const uint8_t *o = shb_textproc_output(s->tp, &nout);
+            s->acc.insert(s->acc.end(), o, o + nout);
+            memmove(s->buf, s->buf + used, n - used);
+            n -= used;
+        }
+        s->rc = rc;
+        s->consumed = off;
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            s->done = seq;
+        }
+        s->cv.notify_all();
+    }
+}
+
 // processSequences (seqhasher.go:210-286) with the loop body on the GPU
-int process_sequences(host::Source &in, FILE *out, const Config &cfg, std::string &err)
+int process_sequences(host::Source &in, FILE *out, const Config &cfg, int n_gpus, std::string &err)
 {
     std::string label = cfg.input;
     bool no_file_name = cfg.no_file_name;
     if (!cfg.name_override.empty()) label = cfg.name_override;
     else if (label == "-") no_file_name = true;   // seqhasher.go:217-219
-    std::vector<int> ids;
+    RunArgs args;
     for (const std::string &t : cfg.hash_types) {
         int id = shb_algo_id(t.c_str());
-        ids.push_back(id < 0 ? SHB_SHA1 : id);    // getHashFunc's default: arm (seqhasher.go:344-346)
+        args.ids.push_back(id < 0 ? SHB_SHA1 : id);    // getHashFunc's default: arm (seqhasher.go:344-346)
     }
-    if (ids.size() > 12) { err = "at most 12 hash types per run are supported by the GPU formatter"; return 1; }
-    size_t cap = (size_t)64 << 20;
+    if (args.ids.size() > 48) { err = "at most 48 hash fields per record are supported by the GPU formatter"; return 1; }
+    args.flags = cfg.case_sensitive ? 0u : SHB_FLAG_UPPER;
+    args.headers_only = cfg.headers_only ? 1 : 0;
+    args.label = no_file_name ? nullptr : label.c_str();
+    size_t base_cap = (size_t)64 << 20;
+    if (const char *e = getenv("SHB_CHUNK_KB")) {   // tests: small chunks exercise the chunk seams and the slot rotation
+        const long kb = atol(e);
+        if (kb >= 1) base_cap = (size_t)kb << 10;
+    }
     phase("before create");
-    shb_textproc *tp = shb_textproc_create(0, cap);
-    if (!tp) { err = std::string("seqhash_b200: ") + shb_last_error(); return 1; }
-    phase("textproc created");
-    uint8_t *buf = shb_textproc_input(tp);
-    const unsigned flags = cfg.case_sensitive ? 0u : SHB_FLAG_UPPER;
-    size_t fill = 0;
-    int format = 0;
+    const int K = 2 * n_gpus;
+    std::vector<std::unique_ptr<Slot>> slots;
+    for (int k = 0; k < K; k++) {
+        slots.emplace_back(new Slot());
+        slots[k]->device = k % n_gpus;   // consecutive chunks go to different GPUs
+    }
+    // slots are created on first use: a small input pays for one set of pinned buffers only
+    auto ensure = [&](Slot &s, size_t need) -> bool {
+        if (s.tp && s.cap > need) return true;
+        size_t ncap = s.tp ? s.cap : base_cap;
+        while (ncap <= need) ncap *= 4;
+        if (ncap > ((size_t)1 << 31)) ncap = (size_t)1 << 31;
+        if (ncap <= need) { err = "Error reading record: record larger than the GPU text buffer"; return false; }
+        shb_textproc *t = shb_textproc_create(s.device, ncap);
+        if (!t) { err = std::string("seqhash_b200: ") + shb_last_error(); return false; }
+        if (s.tp) shb_textproc_destroy(s.tp);
+        s.tp = t;
+        s.cap = ncap;
+        s.buf = shb_textproc_input(t);
+        if (!s.worker.joinable()) s.worker = std::thread(slot_worker, &s, &args);
+        return true;
+    };
+
+    // writer: chunk outputs in chunk order
+    std::mutex wmu;
+    std::condition_variable wcv;
+    long long submitted = -1;        // last chunk sequence handed to a slot
+    bool reader_done = false;
+    int rc = 0;                      // first failure, in chunk order
+    std::atomic<bool> failed{false};
+    std::thread writer([&] {
+        for (long long seq = 0;; seq++) {
+            {
+                std::unique_lock<std::mutex> lk(wmu);
+                wcv.wait(lk, [&] { return submitted >= seq || reader_done; });
+                if (submitted < seq) return;
+            }
+            Slot &s = *slots[seq % K];
+            {
+                std::unique_lock<std::mutex> lk(s.mu);
+                s.cv.wait(lk, [&] { return s.done >= seq; });
+            }
+            if (rc == 0) {
+                if (s.rc < 0) {
+                    err = "Error reading record: " + s.err;
+                    rc = 1;
+                } else {
+                    size_t nout = 0;
+                    const uint8_t *o = shb_textproc_output(s.tp, &nout);
+                    const bool any = shb_textproc_records(s.tp) > 0;
+                    if ((!s.acc.empty() && fwrite(s.acc.data(), 1, s.acc.size(), out) != s.acc.size()) ||
+                        (any && nout && fwrite(o, 1, nout, out) != nout)) {
+                        err = std::string("Error writing record: ") + strerror(errno);
+                        rc = 1;
+                    }
+                    for (size_t k = 0; k < s.n_empty * args.ids.size(); k++) fprintf(stderr, "%s\n", kEmptyMsg);
+                    if (rc == 0 && s.rc == SHB_PARTIAL_FORMAT) {
+                        err = "Error reading record: fastx: invalid FASTA/Q format";
+                        rc = 1;
+                    }
+                }
+                if (rc) failed = true;
+            }
+            {
+                std::lock_guard<std::mutex> lk(s.mu);
+                s.freed = seq;
+            }
+            s.cv.notify_all();
+        }
+    });
+
+    std::vector<uint8_t> carry;      // the unconsumed tail of the previous chunk
     bool eof = false;
-    int rc = 0;
     std::string read_err;
-    while (true) {
-        while (!eof && fill < cap) {
+    long long seq = 0;
+    int setup_rc = 0;
+    while (!failed) {
+        Slot &s = *slots[seq % K];
+        if (seq >= K) {   // wait until the slot's previous chunk has been written
+            std::unique_lock<std::mutex> lk(s.mu);
+            s.cv.wait(lk, [&] { return s.freed >= seq - K; });
+        }
+        if (!ensure(s, carry.size())) { setup_rc = 1; break; }
+        if (seq == 0) phase("textproc created");
+        size_t fill = carry.size();
+        if (fill) memcpy(s.buf, carry.data(), fill);
+        carry.clear();
+        while (!eof && fill < s.cap) {
             size_t got = 0;
             try {
-                got = in.read(buf + fill, cap - fill);
+                got = in.read(s.buf + fill, s.cap - fill);
             } catch (const std::exception &e) {
                 // A damaged or truncated input: the records that are complete in what was decoded before the
                 // failure are still written (as a non-final chunk), then the error is reported — the reference's
@@ -174,65 +369,112 @@ int process_sequences(host::Source &in, FILE *out, const Config &cfg, std::strin
             if (got == 0) eof = true;
             fill += got;
         }
-        if (format == 0) {   // fastx.NewReaderFromIO sniffs the first non-blank byte (seqhasher.go:221)
+        if (args.format == 0) {   // fastx.NewReaderFromIO sniffs the first non-blank byte (seqhasher.go:221)
             size_t skip = 0;
-            while (skip < fill && is_blank(buf[skip])) skip++;
+            while (skip < fill && is_blank(s.buf[skip])) skip++;
             if (skip == fill) {
                 if (eof) break;   // empty input: no records
-                fill = 0;
-                continue;
+                continue;         // nothing but blank space so far: read on (same slot, same sequence number)
             }
-            if (buf[skip] == '>') format = SHB_FORMAT_FASTA;
-            else if (buf[skip] == '@') format = SHB_FORMAT_FASTQ;
-            else { err = "Failed to create reader: fastx: invalid FASTA/Q format"; rc = 1; break; }
-            memmove(buf, buf + skip, fill - skip);
+            if (s.buf[skip] == '>') args.format = SHB_FORMAT_FASTA;
+            else if (s.buf[skip] == '@') args.format = SHB_FORMAT_FASTQ;
+            else { err = "Failed to create reader: fastx: invalid FASTA/Q format"; setup_rc = 1; break; }
+            memmove(s.buf, s.buf + skip, fill - skip);
             fill -= skip;
         }
         if (eof) {
-            while (fill > 0 && is_blank(buf[fill - 1])) fill--;   // trailing blank lines are not records
+            while (fill > 0 && is_blank(s.buf[fill - 1])) fill--;   // trailing blank lines are not records
             if (fill == 0) break;
         }
-        if (shb_textproc_run(tp, fill, format, (eof && read_err.empty()) ? 1 : 0, ids.empty() ? nullptr : ids.data(), (int)ids.size(), flags,
-                             cfg.headers_only ? 1 : 0, no_file_name ? nullptr : label.c_str()) < 0) {
-            err = std::string("Error reading record: ") + shb_last_error();
-            rc = 1;
-            break;
+        const bool last = eof;
+        size_t cut = fill;
+        s.whole = true;
+        s.is_final = true;
+        if (!(eof && read_err.empty())) {
+            cut = find_cut(s.buf, fill, args.format);
+            if (cut == 0) {       // one record fills the buffer (or FASTQ line structure unclear): let the GPU say how far it got
+                cut = fill;
+                s.whole = false;
+                s.is_final = false;
+            } else {
+                carry.assign(s.buf + cut, s.buf + fill);
+            }
         }
-        size_t nout = 0;
-        const uint8_t *o = shb_textproc_output(tp, &nout);
-        if (nout && fwrite(o, 1, nout, out) != nout) { err = "Error writing record: short write"; rc = 1; break; }
-        for (size_t k = 0; k < shb_textproc_empty_records(tp) * ids.size(); k++) fprintf(stderr, "%s\n", kEmptyMsg);
-        if (eof) break;
-        const size_t used = shb_textproc_consumed(tp);
-        if (used == 0) {   // one record larger than the buffer: grow it
-            if (cap >= ((size_t)1 << 31)) { err = "Error reading record: record larger than the GPU text buffer"; rc = 1; break; }
-            size_t ncap = cap * 4 > ((size_t)1 << 31) ? ((size_t)1 << 31) : cap * 4;
-            shb_textproc *bigger = shb_textproc_create(0, ncap);
-            if (!bigger) { err = std::string("seqhash_b200: ") + shb_last_error(); rc = 1; break; }
-            memcpy(shb_textproc_input(bigger), buf, fill);
-            shb_textproc_destroy(tp);
-            tp = bigger;
-            buf = shb_textproc_input(tp);
-            cap = ncap;
-            continue;
+        s.n_bytes = cut;
+        {
+            std::lock_guard<std::mutex> lk(s.mu);
+            s.ready = seq;
         }
-        memmove(buf, buf + used, fill - used);
-        fill -= used;
+        s.cv.notify_all();
+        {
+            std::lock_guard<std::mutex> lk(wmu);
+            submitted = seq;
+        }
+        wcv.notify_all();
+        if (!s.whole) {   // serial step: the next chunk starts where this one stopped
+            std::unique_lock<std::mutex> lk(s.mu);
+            s.cv.wait(lk, [&] { return s.done >= seq; });
+            if (s.rc >= 0) {
+                const size_t used = s.consumed;
+                carry.assign(s.buf + used, s.buf + fill);   // used == 0: the next slot is grown to hold it
+                if (used == 0 && last) { seq++; break; }      // nothing more will come: an unfinished record at a damaged end
+            }
+        }
+        seq++;
+        if (last) break;
     }
+    {
+        std::lock_guard<std::mutex> lk(wmu);
+        reader_done = true;
+    }
+    wcv.notify_all();
+    writer.join();
+    for (auto &sp : slots) {
+        {
+            std::lock_guard<std::mutex> lk(sp->mu);
+            sp->quit = true;
+        }
+        sp->cv.notify_all();
+        if (sp->worker.joinable()) sp->worker.join();
+    }
+    if (rc == 0 && setup_rc) rc = setup_rc;
     if (rc == 0 && !read_err.empty()) { err = read_err; rc = 1; }
-    fflush(out);
+    if (fflush(out) != 0 || ferror(out)) {
+        if (rc == 0) { err = std::string("Error writing record: ") + strerror(errno); rc = 1; }
+    }
     phase("records done");
     // no shb_textproc_destroy: unpinning the staging buffers costs about a second and the process is exiting
     return rc;
+}
+
+// How many GPUs this run uses: SHB_GPUS if set; otherwise one per 2 GiB of a plain regular file (creating a CUDA
+// context costs 0.1-0.25 s per device, one GPU runs the record loop at about 13 GB/s of text), one for anything else
+// (a compressed input is bound by its host-side inflate, not by the GPU).
+int pick_gpus(FILE *fin, bool regular_plain)
+{
+    if (const char *e = getenv("SHB_GPUS")) {
+        const int v = atoi(e);
+        if (v > 0) return v;
+    }
+    if (!regular_plain) return 1;
+    struct stat st;
+    if (fstat(fileno(fin), &st) != 0 || !S_ISREG(st.st_mode)) return 1;
+    const long long per = 2LL << 30;
+    long long n = (st.st_size + per - 1) / per;
+    return (int)(n < 1 ? 1 : n > 8 ? 8 : n);
+}
+
+std::string go_errno_text(int e)
+{
+    std::string t = strerror(e);
+    if (!t.empty() && t[0] >= 'A' && t[0] <= 'Z') t[0] = (char)(t[0] - 'A' + 'a');   // Go's syscall error texts are lower-case
+    return t;
 }
 
 }  // namespace
 
 int main(int argc, char **argv)
 {
-    // This process uses one GPU.  Unless the caller chose, hide the others: creating the CUDA context otherwise
-    // initialises every device of the node (about 0.1 s each on an 8-GPU box) for a run that lasts half a second.
-    setenv("CUDA_VISIBLE_DEVICES", "0", 0);
     Config cfg;
     std::string err;
     switch (parse_flags(argc, argv, cfg, err)) {
@@ -259,14 +501,14 @@ int main(int argc, char **argv)
     }
     FILE *fin = cfg.input == "-" ? stdin : fopen(cfg.input.c_str(), "rb");
     if (!fin) {
-        fprintf(stderr, "Error opening input: open %s: no such file or directory\n", cfg.input.c_str());
+        fprintf(stderr, "Error opening input: open %s: %s\n", cfg.input.c_str(), go_errno_text(errno).c_str());
         return 1;
     }
     FILE *fout = stdout;
     if (!cfg.output.empty() && cfg.output != "-") {
         fout = fopen(cfg.output.c_str(), "wb");
         if (!fout) {
-            fprintf(stderr, "Error opening output: open %s: no such file or directory\n", cfg.output.c_str());
+            fprintf(stderr, "Error opening output: open %s: %s\n", cfg.output.c_str(), go_errno_text(errno).c_str());
             return 1;
         }
     }
@@ -274,8 +516,23 @@ int main(int argc, char **argv)
     setvbuf(fout, obuf, _IOFBF, sizeof obuf);
     int rc = 1;
     try {
-        auto src = host::open_maybe_compressed(fin, fin != stdin);
-        rc = process_sequences(*src, fout, cfg, err);
+        bool compressed = false;
+        auto src = host::open_maybe_compressed(fin, fin != stdin, &compressed);
+        int n_gpus = pick_gpus(fin, fin != stdin && !compressed);
+        // Unless the caller chose, hide the GPUs this run does not use: creating the CUDA context otherwise initialises
+        // every device of the node (about 0.1 s each on an 8-GPU box) for a run that may last half a second.
+        if (!getenv("CUDA_VISIBLE_DEVICES")) {
+            std::string vis;
+            for (int d = 0; d < n_gpus; d++) vis += (d ? "," : "") + std::to_string(d);
+            setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
+        }
+        const int have = shb_init(0, 0);
+        if (have <= 0) {
+            err = std::string("seqhash_b200: ") + shb_last_error();
+        } else {
+            if (n_gpus > have) n_gpus = have;
+            rc = process_sequences(*src, fout, cfg, n_gpus, err);
+        }
     } catch (const std::exception &e) {
         err = std::string("Error reading record: ") + e.what();
         rc = 1;

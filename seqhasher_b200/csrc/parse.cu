@@ -298,19 +298,19 @@ __global__ void __launch_bounds__(FX_THREADS) fx_emit_kernel(const uint8_t *__re
         if (le > line_start && text[le - 1] == '\r') le--;
         if ((ev_mask >> j) & 1u) {
             const long long r = rec_run++;
+            if (r <= out.max_records) {                     // offsets / rec_start hold max_records + 1 entries: the
+                out.offsets[r] = kept_here;                 // record after the last indexed one marks where to resume
+                out.rec_start[r] = line_start;              // (nothing of a name line is ever kept)
+            }
             if (r < out.max_records) {
                 out.name_start[r] = line_start + 1;         // skip '>' / '@'
                 out.name_len[r] = (int)(le - line_start - 1 > 0 ? le - line_start - 1 : 0);
-                out.offsets[r] = kept_here;                 // nothing of a name line is ever kept
-                out.rec_start[r] = line_start;
-                if (text[line_start] != (FASTQ ? '@' : '>')) info->status = FX_BAD_MARKER;
-            } else {
-                info->status = FX_TOO_MANY_RECORDS;
+                if (text[line_start] != (FASTQ ? '@' : '>')) atomicMin(reinterpret_cast<unsigned long long *>(&info->first_bad), (unsigned long long)r);
             }
         } else if (FASTQ) {
             const long long kind = line_no & 3;
             const long long r = rec_run - 1;                // the record this line belongs to
-            if (kind == 2 && text[line_start] != '+') info->status = FX_BAD_MARKER;
+            if (kind == 2 && text[line_start] != '+' && r >= 0) atomicMin(reinterpret_cast<unsigned long long *>(&info->first_bad), (unsigned long long)r);
             if (kind == 3 && r >= 0 && r < out.max_records) {
                 out.qual_start[r] = line_start;
                 out.qual_len[r] = (int)(le - line_start);
@@ -341,18 +341,27 @@ __global__ void fx_finish_kernel(const long long *__restrict__ kept_prefix, cons
                                  const long long *__restrict__ nl_before, const long long *__restrict__ prev_nl, size_t nb,
                                  size_t n, int fastq, int is_final, FxOut out, FxInfo *__restrict__ info)
 {
-    long long n_ev = rec_prefix[nb];
-    if (n_ev > out.max_records) { n_ev = out.max_records; info->status = FX_TOO_MANY_RECORDS; }
+    const long long n_ev = rec_prefix[nb];
     const long long kept = kept_prefix[nb];
-    long long nrec, consumed;
-    if (fastq) {
+    long long nrec, consumed, status = FX_OK;
+    if (n_ev > out.max_records) {
+        // The record index is full: hand back the first max_records records (all complete: the name line of the next
+        // one was seen, and a FASTQ record's four lines precede it) and let the caller resume at the next record.
+        nrec = out.max_records;
+        consumed = out.rec_start[nrec];
+        status = FX_MORE;
+    } else if (fastq) {
         const long long lines = nl_before[nb];
         nrec = lines / 4 < n_ev ? lines / 4 : n_ev;
         if (nrec == n_ev) {          // every record whose name line ended is complete
             out.offsets[nrec] = kept;
             consumed = is_final ? (long long)n : prev_nl[nb] + 1;   // up to the last line break
+            // the input ends inside a record (1-3 stray lines after the last complete one): the reader of the reference
+            // fails on it after yielding the records before
+            if (is_final && (lines & 3) != 0) { status = FX_BAD_MARKER; consumed = prev_nl[nb] + 1; }
         } else {
             consumed = out.rec_start[nrec];   // offsets[nrec] was written by the incomplete record's event
+            if (is_final) status = FX_BAD_MARKER;   // truncated last record
         }
     } else if (is_final) {
         nrec = n_ev;
@@ -363,10 +372,19 @@ __global__ void fx_finish_kernel(const long long *__restrict__ kept_prefix, cons
         consumed = n_ev > 0 ? out.rec_start[nrec] : 0;
         if (n_ev == 0) out.offsets[0] = 0;
     }
-    if (nrec == 0) out.offsets[0] = 0;
+    const long long bad = info->first_bad;
+    if (bad >= 0 && bad < nrec) {             // a malformed record inside the chunk: keep what precedes it
+        nrec = bad;
+        consumed = out.rec_start[bad];
+        status = FX_BAD_MARKER;
+    } else if (bad == nrec && bad < n_ev) {   // ... or right after the complete ones
+        status = FX_BAD_MARKER;
+    }
+    if (nrec == 0 && n_ev == 0) out.offsets[0] = 0;
     info->n_records = nrec;
     info->n_residues = out.offsets[nrec];
     info->consumed = consumed;
+    info->status = status;
 }
 
 // ------------------------------------------------------------------------------------------- formatter
@@ -494,6 +512,7 @@ cudaError_t launch_fx_parse(const uint8_t *text, size_t n, bool fastq, bool is_f
     long long *tile_before = reinterpret_cast<long long *>(p);
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(FxInfo), st);
     if (e != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(&info->first_bad, 0x7f, sizeof(long long), st)) != cudaSuccess) return e;   // "none"
     if (fastq && (e = cudaMemsetAsync(out.qual_len, 0, (size_t)out.max_records * sizeof(int), st)) != cudaSuccess) return e;
     fx_lines_kernel<<<(unsigned)nb, FX_THREADS, 0, st>>>(text, n, last_nl, nl_count);
     if (nb <= 4096) {

@@ -9,7 +9,10 @@
 namespace shb {
 
 constexpr uint32_t FX_BLK = 4096;
-enum : long long { FX_OK = 0, FX_BAD_MARKER = 1, FX_TOO_MANY_RECORDS = 2 };
+// FX_BAD_MARKER: the text at `consumed` is not a valid record (FASTQ '@' / '+' markers, a truncated last record);
+// the n_records before it are complete and usable.  FX_MORE: the record index is full — the chunk was cut after
+// max_records records and the caller runs the rest (from `consumed`) as another chunk.
+enum : long long { FX_OK = 0, FX_BAD_MARKER = 1, FX_MORE = 2 };
 
 struct FxInfo {            // device-side result block
     long long n_records;   // complete records
@@ -18,6 +21,7 @@ struct FxInfo {            // device-side result block
     long long consumed;    // bytes of the text covered by the complete records
     long long n_empty;     // records whose sequence is empty (formatter)
     long long reserved;
+    long long first_bad;   // index of the first malformed record (LLONG_MAX: none); set by the splitter
 };
 
 struct FxOut {
@@ -31,12 +35,13 @@ struct FxOut {
     long long max_records;
 };
 
+constexpr int FMT_MAX_FIELDS = 48;   // hash fields per output record ("--hash" may repeat names, seqhasher.go:132-137)
 struct FmtCfg {
     const uint8_t *label;    // device copy of the file label
     int label_len;           // -1: no file name field
     int n_algos;
-    int dsize[N_ALGOS];
-    const uint8_t *digests[N_ALGOS];
+    int dsize[FMT_MAX_FIELDS];
+    const uint8_t *digests[FMT_MAX_FIELDS];
     int headers_only, fastq, upper;
 };
 

@@ -124,7 +124,10 @@ def read_records(stream):
             plus = f.readline()
             if plus[:1] != b"+":
                 raise FastxError(ERR_INVALID)
-            qual = _strip_eol(f.readline())
+            qline = f.readline()
+            if not qline:            # the input ends inside the record (no quality line at all)
+                raise FastxError(ERR_INVALID)
+            qual = _strip_eol(qline)
             yield Record(name, seq, qual)
             line = f.readline()
     else:

@@ -69,7 +69,9 @@ def process_sequences_gpu(input_stream, output_stream, cfg, textproc=None, chunk
     """processSequences with the WHOLE record loop on the GPU (shb_textproc): the host only decompresses and
     moves bytes.  Same observable behaviour as process_sequences (output text, error texts, one stderr line
     per empty record and hash type)."""
+    import lzma
     import sys
+    import zlib
 
     from .. import binding as B
     from .fastx import ERR_INVALID, open_maybe_compressed
@@ -82,42 +84,55 @@ def process_sequences_gpu(input_stream, output_stream, cfg, textproc=None, chunk
     elif label == "-":
         no_file_name = True   # seqhasher.go:217-219
     own = textproc is None
-    if len(cfg.hash_types) > 12:
-        # the GPU formatter carries at most 12 hash fields; longer lists take the host-side loop
+    if len(cfg.hash_types) > 48:
+        # the GPU formatter carries at most 48 hash fields; longer lists take the host-side loop
         return process_sequences(input_stream, output_stream, cfg)
     tp = textproc or B.TextProc(chunk_bytes)
     ids = _algo_ids(cfg.hash_types)
     flags = 0 if cfg.case_sensitive else B.FLAG_UPPER
-    f = open_maybe_compressed(input_stream)
+    blanks = b" \t\n\v\f\r"
+
+    def fail_read(e):
+        return RuntimeError(f"Error reading record: {e}")
+
     try:
+        f = open_maybe_compressed(input_stream)
         fill = 0          # bytes currently in tp.input
         fmt = 0
         eof = False
         while True:
             while not eof and fill < tp.capacity:
-                if hasattr(f, "readinto"):      # straight into the pinned buffer: no intermediate bytes object
-                    got = f.readinto(memoryview(tp.input)[fill: tp.capacity])
-                    if not got:
-                        eof = True
-                        break
-                    fill += got
-                else:
-                    chunk = f.read(tp.capacity - fill)
-                    if not chunk:
-                        eof = True
-                        break
-                    tp.input[fill: fill + len(chunk)] = memoryview(chunk)
-                    fill += len(chunk)
+                try:
+                    if hasattr(f, "readinto"):      # straight into the pinned buffer: no intermediate bytes object
+                        got = f.readinto(memoryview(tp.input)[fill: tp.capacity])
+                        if not got:
+                            eof = True
+                            break
+                        fill += got
+                    else:
+                        chunk = f.read(tp.capacity - fill)
+                        if not chunk:
+                            eof = True
+                            break
+                        tp.input[fill: fill + len(chunk)] = memoryview(chunk)
+                        fill += len(chunk)
+                except (EOFError, OSError, ValueError, zlib.error, lzma.LZMAError) as e:   # damaged / truncated compressed input
+                    raise fail_read(e) from None
             if fmt == 0:
                 # sniff: skip leading blank space, first byte decides (fastx.NewReaderFromIO, seqhasher.go:221)
-                head = bytes(tp.input[:fill])
-                skip = len(head) - len(head.lstrip())
+                skip = 0
+                while skip < fill:
+                    head = bytes(tp.input[skip: min(fill, skip + 4096)])
+                    k = len(head) - len(head.lstrip(blanks))
+                    skip += k
+                    if k < len(head):
+                        break
                 if skip == fill:
                     if eof:
                         return          # empty input: no records
                     fill = 0
                     continue
-                first = head[skip: skip + 1]
+                first = bytes(tp.input[skip: skip + 1])
                 if first == b">":
                     fmt = B.FORMAT_FASTA
                 elif first == b"@":
@@ -129,25 +144,29 @@ def process_sequences_gpu(input_stream, output_stream, cfg, textproc=None, chunk
                     fill -= skip
             if eof:
                 # trailing blank lines are not records
-                tail = bytes(tp.input[max(0, fill - 4096): fill])
-                fill -= len(tail) - len(tail.rstrip())
+                while fill:
+                    tail = bytes(tp.input[max(0, fill - 4096): fill])
+                    k = len(tail) - len(tail.rstrip(blanks))
+                    fill -= k
+                    if k < len(tail):
+                        break
                 if fill == 0:
                     return
             try:
                 out, consumed, nrec, nempty = tp.run(fill, fmt, eof, ids, flags, cfg.headers_only,
                                                      None if no_file_name else label.encode())
             except B.SeqhashError as e:
-                if ERR_INVALID in str(e):
-                    raise RuntimeError(f"Error reading record: {ERR_INVALID}") from None
-                raise
+                raise fail_read(ERR_INVALID if ERR_INVALID in str(e) else e) from None
             for _ in range(nempty * len(ids)):
                 print(EMPTY_MSG, file=log)
             output_stream.write(memoryview(out))
-            if eof:
+            if tp.partial_format:       # the records before the malformed one have been written
+                raise fail_read(ERR_INVALID)
+            if eof and consumed >= fill:
                 return
             if consumed == 0:
                 # one record does not fit the text buffer (e.g. a chromosome): grow the buffer and retry
-                if not own or tp.capacity >= (1 << 31):
+                if eof or not own or tp.capacity >= (1 << 31):
                     raise RuntimeError("Error reading record: record larger than the GPU text buffer")
                 bigger = B.TextProc(min(tp.capacity * 4, 1 << 31))
                 bigger.input[:fill] = tp.input[:fill]

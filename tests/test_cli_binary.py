@@ -151,3 +151,103 @@ def test_binary_truncated_gzip_writes_complete_records_then_fails(tmp_path):
     got = out.encode()
     want = _expected_headers(recs)
     assert len(got) > len(want) // 2 and want.startswith(got)
+
+
+def run_env(args, env, stdin=None, cwd=FIX):
+    e = dict(os.environ)
+    e.update(env)
+    p = subprocess.run([BIN] + args, input=stdin, capture_output=True, cwd=cwd, timeout=300, env=e)
+    return p.returncode, p.stdout, p.stderr.decode()
+
+
+@pytest.mark.gpu
+def test_binary_more_records_than_the_index_holds(tmp_path):
+    """5 M five-byte records in one 64 MB chunk: more than the record index of a chunk (capacity / 16 + 1024) holds.
+    The chunk is consumed in several passes (this used to fail with 'use smaller chunks')."""
+    import hashlib
+    n = 5_000_000
+    bases = b"ACGT"
+    text = b"".join(b">%d\n%c\n" % (i % 10, bases[i & 3]) for i in range(n))
+    p = tmp_path / "tiny.fa"
+    p.write_bytes(text)
+    rc, out, err = run_env(["--headersonly", "--nofilename", str(p), "-"], {})
+    assert rc == 0, err
+    h = [hashlib.sha1(bytes([b])).hexdigest().encode() for b in bases]
+    lines = out.split(b"\n")
+    assert len(lines) == n + 1 and lines[-1] == b""
+    assert lines[0] == h[0] + b";0" and lines[1234567] == h[1234567 & 3] + b";7" and lines[n - 1] == h[(n - 1) & 3] + b";9"
+    import collections
+    c = collections.Counter(lines[:-1])
+    assert len(c) == 20 and sum(c.values()) == n   # ids 0-9 x bases 0-3 pair up as (i % 10, i & 3): 20 combinations
+
+
+@pytest.mark.gpu
+def test_binary_truncated_fastq_fails_after_the_complete_records(tmp_path):
+    """The input ends inside a FASTQ record: the records before it are written, then the reader's error, rc 1
+    (the tail used to vanish with rc 0)."""
+    t = S1["ACTG"]
+    for tail in (b"@r2\nAC", b"@r2\nACGT\n", b"@r2\nACGT\n+\n", b"@r2\nACGT\n+"):
+        rc, out, err = run_env(["--nofilename", "-", "-"], {}, stdin=b"@r1\nACTG\n+\nIIII\n" + tail)
+        assert rc == 1, tail
+        assert out == f"@{t};r1\nACTG\n+\nIIII\n".encode(), tail
+        assert err.strip() == "Error reading record: fastx: invalid FASTA/Q format", tail
+    # a bad '+' line in the middle of the text: everything before that record is kept
+    rc, out, err = run_env(["--nofilename", "--headersonly", "-", "-"], {},
+                           stdin=b"@r1\nACTG\n+\nIIII\n@r2\nACTG\nX\nIIII\n@r3\nACTG\n+\nIIII\n")
+    assert rc == 1 and out == f"{t};r1\n".encode() and "invalid FASTA/Q format" in err
+
+
+@pytest.mark.gpu
+def test_binary_small_chunks_pipeline_matches_one_chunk(tmp_path):
+    """The chunk pipeline (reader -> 2 slots per GPU -> ordered writer) with 256 KiB chunks — hundreds of seams,
+    records carried across them — against the same file in one chunk; FASTA (wrapped) and FASTQ (quality lines that
+    start with '@' and '+')."""
+    import numpy as np
+    recs, text = _records(20_000, seed=33, wrap=60)
+    p = tmp_path / "a.fa"
+    p.write_bytes(text)
+    rc, one, err = run_env(["--hash", "sha1,xxh3", str(p), "-"], {})
+    assert rc == 0, err
+    rc, many, err = run_env(["--hash", "sha1,xxh3", str(p), "-"], {"SHB_CHUNK_KB": "256"})
+    assert rc == 0, err
+    assert many == one
+    r = np.random.default_rng(4)
+    fq = []
+    for i in range(30_000):
+        L = int(r.integers(20, 300))
+        s = r.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=L).tobytes()
+        q = r.choice(np.frombuffer(b"@+!I5", dtype=np.uint8), size=L).tobytes()
+        fq.append(b"@q%d x\n%s\n+\n%s\n" % (i, s, q))
+    fq = b"".join(fq)
+    rc, one, err = run_env(["--hash", "md5", "-", "-"], {}, stdin=fq)
+    assert rc == 0, err
+    rc, many, err = run_env(["--hash", "md5", "-", "-"], {"SHB_CHUNK_KB": "64"}, stdin=fq)
+    assert rc == 0, err
+    assert many == one and one.count(b"\n") == 4 * 30_000
+
+
+@pytest.mark.gpu
+def test_binary_two_gpus_match_one(tmp_path):
+    """SHB_GPUS=2: chunks alternate between two devices, output order = chunk order (byte-identical to one GPU)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    recs, text = _records(60_000, seed=12, wrap=80)
+    p = tmp_path / "b.fa"
+    p.write_bytes(text)
+    rc, one, err = run_env(["--hash", "sha1,blake3,nthash", str(p), "-"], {"SHB_GPUS": "1", "SHB_CHUNK_KB": "4096"})
+    assert rc == 0, err
+    rc, two, err = run_env(["--hash", "sha1,blake3,nthash", str(p), "-"], {"SHB_GPUS": "2", "SHB_CHUNK_KB": "4096"})
+    assert rc == 0, err
+    assert two == one
+
+
+def test_binary_open_errors_use_the_errno_text(tmp_path):
+    d = tmp_path / "dir.fa"
+    d.mkdir()
+    rc, _, err = run([str(tmp_path / "missing.fa")])
+    assert rc == 1 and err.strip().endswith("no such file or directory")
+    rc, _, err = run(["test.fasta", str(tmp_path / "nodir" / "out.fa")])
+    assert rc == 1 and err.startswith("Error opening output: open ") and err.strip().endswith("no such file or directory")
+    rc, _, err = run(["test.fasta", str(d)])
+    assert rc == 1 and err.strip().endswith("is a directory")

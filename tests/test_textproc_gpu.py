@@ -236,3 +236,33 @@ def test_random_text_soak(H, oracle, seed):
         got = run_gpu(H, data, cfg, chunk=chunk)
         want = expected(oracle, data, cfg)
         assert got == want, (seed, it, fastq, kw, chunk, len(data))
+
+
+def test_more_records_than_the_chunk_index(H, oracle):
+    """A 64 KiB text buffer indexes 64 Ki / 16 + 1024 = 5120 records; 30 000 six-byte records per chunk make every
+    chunk overflow it, so each is consumed over several runs (used to fail with SHB_ERR_CAPACITY)."""
+    data = b"".join(b">%d\n%s\n" % (i % 7, (b"A", b"CG", b"T", b"")[i & 3]) for i in range(30_000))
+    cfg = H.Config(hash_types=["md5"], headers_only=True, no_file_name=True, input_file_name="t")
+    assert run_gpu(H, data, cfg, chunk=1 << 16) == expected(oracle, data, cfg)
+    fq = b"".join(b"@%d\n%s\n+\n%s\n" % (i % 7, b"ACGT"[: 1 + (i & 3)], b"IIII"[: 1 + (i & 3)]) for i in range(20_000))
+    assert run_gpu(H, fq, cfg, chunk=1 << 16) == expected(oracle, fq, cfg)
+
+
+@pytest.mark.parametrize("tail", [b"@r2\nAC", b"@r2\nACGT\n", b"@r2\nACGT\n+\n", b"@r2\nACGT\n+"])
+def test_truncated_fastq_is_an_error_after_the_complete_records(H, tail):
+    """a FASTQ input that ends inside a record lost that record silently (rc 0)."""
+    from seqhasher_b200 import binding as B
+    cfg = H.Config(hash_types=["sha1"], no_file_name=True, input_file_name="q")
+    out = io.BytesIO()
+    tp = B.TextProc(1 << 16)
+    try:
+        with pytest.raises(RuntimeError) as e:
+            H.process_sequences_gpu(io.BytesIO(b"@r1\nACTG\n+\nIIII\n" + tail), out, cfg, textproc=tp, log=io.StringIO())
+    finally:
+        tp.close()
+    assert str(e.value) == "Error reading record: fastx: invalid FASTA/Q format"
+    assert out.getvalue() == b"@65c89f59d38cdbf90dfaf0b0a6884829df8396b0;r1\nACTG\n+\nIIII\n"
+    # the host reader mirror agrees
+    from seqhasher_b200.host.fastx import FastxError, read_records
+    with pytest.raises(FastxError):
+        list(read_records(io.BytesIO(b"@r1\nACTG\n+\nIIII\n" + tail)))
