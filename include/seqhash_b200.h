@@ -42,6 +42,12 @@ enum shb_algo {
 #define SHB_FLAG_UPPER 1u     /* ASCII a-z -> A-Z: seqhasher.go:249-251 (set unless --casesensitive) */
 #define SHB_FLAG_STRIP 2u     /* drop \t \n \v \f \r ' ': seqhasher.go:246 */
 #define SHB_FLAG_EMIT_SEQ 4u  /* also return the normalised sequences (record.Seq.Seq = seq, :252) */
+/* Non-ASCII input.  For a record that holds a byte >= 0x80 the reference's bytes.Fields / bytes.ToUpper switch to Unicode
+ * rules (UTF-8 decoding, Unicode spaces, rune-wise upper-casing that re-encodes invalid bytes as U+FFFD: seqhasher.go:243-251;
+ * its README declares such input unsupported).  This engine is byte-wise ASCII: such bytes are hashed as they are.  A host
+ * that cannot vouch for ASCII input sets SHB_FLAG_CHECK_ASCII (one more pass over the residues) and refuses the batch when
+ * shb_batch_nonascii() is not 0; shb_textproc counts them for free (shb_textproc_nonascii). */
+#define SHB_FLAG_CHECK_ASCII 8u
 /* Path override for cross-checking (tests): the library normally picks the kernel family from the mean record
  * length; these force the thread-per-record direct kernels / forbid the long-record kernels. */
 #define SHB_FLAG_FORCE_DIRECT 0x100u
@@ -109,6 +115,7 @@ int shb_wait(shb_batch *b);
  * (what the reference writes back to record.Seq.Seq at seqhasher.go:252 for full-record output). */
 const uint8_t *shb_digests(shb_batch *b, int slot);
 const int64_t *shb_out_lengths(shb_batch *b);
+size_t shb_batch_nonascii(shb_batch *b);   /* residue bytes >= 0x80 in the batch (SHB_FLAG_CHECK_ASCII), else 0 */
 const int64_t *shb_out_offsets(shb_batch *b);
 const uint8_t *shb_out_residues(shb_batch *b);
 
@@ -158,6 +165,9 @@ const uint8_t *shb_textproc_output(shb_textproc *t, size_t *out_bytes);
 size_t shb_textproc_consumed(shb_textproc *t);
 size_t shb_textproc_records(shb_textproc *t);
 size_t shb_textproc_empty_records(shb_textproc *t);
+/* sequence bytes >= 0x80 seen in the last chunk (whole chunk, also its unconsumed tail): not 0 means the output may differ
+ * from the reference's, which normalises such records with Unicode rules (seqhasher.go:243-251); the hosts refuse the input */
+size_t shb_textproc_nonascii(shb_textproc *t);
 /* device time of the last run, ms: H2D copy, record split, hashes, formatting (incl. its host syncs), D2H copy */
 void shb_textproc_last_ms(shb_textproc *t, float *ms5);
 

@@ -20,6 +20,7 @@ DIGEST_SIZES = [20, 64, 16, 8, 8, 16, 16, 8, 32, 128, 8, 4]
 FLAG_UPPER = 1
 FLAG_STRIP = 2
 FLAG_EMIT_SEQ = 4
+FLAG_CHECK_ASCII = 8
 FLAG_FORCE_DIRECT = 0x100
 FLAG_NO_LONG_PATH = 0x200
 FLAG_NO_LENGTH_SORT = 0x400
@@ -29,7 +30,7 @@ EXPORTS = [
     "shb_init", "shb_shutdown", "shb_last_error", "shb_version", "shb_algo_id", "shb_algo_name",
     "shb_digest_size", "shb_batch_create", "shb_batch_create_on", "shb_batch_destroy", "shb_batch_residues",
     "shb_batch_offsets", "shb_submit", "shb_wait", "shb_digests", "shb_out_lengths", "shb_out_offsets",
-    "shb_out_residues", "shb_scratch_bytes", "shb_hash_device", "shb_launch_count", "shb_synth_fill",
+    "shb_out_residues", "shb_batch_nonascii", "shb_textproc_nonascii", "shb_scratch_bytes", "shb_hash_device", "shb_launch_count", "shb_synth_fill",
     "shb_probe_int_peak", "shb_probe_last_checksum", "shb_textproc_create", "shb_textproc_destroy",
     "shb_textproc_input", "shb_textproc_capacity", "shb_textproc_run", "shb_textproc_output", "shb_textproc_consumed",
     "shb_textproc_records", "shb_textproc_empty_records", "shb_textproc_last_ms",
@@ -74,6 +75,8 @@ def lib() -> ctypes.CDLL:
     L.shb_out_lengths.argtypes = [c.c_void_p]; L.shb_out_lengths.restype = c.c_void_p
     L.shb_out_offsets.argtypes = [c.c_void_p]; L.shb_out_offsets.restype = c.c_void_p
     L.shb_out_residues.argtypes = [c.c_void_p]; L.shb_out_residues.restype = c.c_void_p
+    L.shb_batch_nonascii.argtypes = [c.c_void_p]; L.shb_batch_nonascii.restype = c.c_size_t
+    L.shb_textproc_nonascii.argtypes = [c.c_void_p]; L.shb_textproc_nonascii.restype = c.c_size_t
     L.shb_scratch_bytes.argtypes = [c.c_size_t, c.c_size_t]; L.shb_scratch_bytes.restype = c.c_size_t
     L.shb_hash_device.argtypes = [c.c_int, c.c_void_p, c.c_void_p, c.c_size_t, c.c_size_t, c.POINTER(c.c_int), c.c_int,
                                   c.c_uint, c.POINTER(c.c_void_p), c.c_void_p, c.c_void_p, c.c_void_p]
@@ -179,6 +182,10 @@ class Batch:
             return np.zeros((0, ds), dtype=np.uint8)
         return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(self.n, ds))
 
+    def nonascii(self) -> int:
+        """residue bytes >= 0x80 of the last batch (submit with FLAG_CHECK_ASCII)"""
+        return lib().shb_batch_nonascii(self._h)
+
     def out_lengths(self) -> np.ndarray:
         p = lib().shb_out_lengths(self._h)
         if self.n == 0:
@@ -279,6 +286,7 @@ class TextProc:
         rc = L.shb_textproc_run(self._h, n_bytes, fmt, 1 if is_final else 0, arr, len(ids), flags,
                                 1 if headers_only else 0, label)
         _check(rc, "shb_textproc_run")
+        self.nonascii = L.shb_textproc_nonascii(self._h)   # sequence bytes >= 0x80 in this chunk
         self.partial_format = rc == PARTIAL_FORMAT   # the text at `consumed` is malformed; the output holds what precedes it
         nb = ctypes.c_size_t(0)
         p = L.shb_textproc_output(self._h, ctypes.byref(nb))

@@ -19,6 +19,40 @@ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnels
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int r) { return __funnelshift_r(x, x, r); }
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
 __device__ __forceinline__ uint64_t rotr64(uint64_t x, int r) { return (x >> r) | (x << (64 - r)); }
+// 64-bit rotate as two funnel shifts (SHF, ALU pipe), r a compile-time constant in 1..63.  Written with the intrinsic because
+// ptxas turns the portable (x << r) | (x >> (64 - r)) form into IMAD.WIDE / IMAD.U32 by 2^r when it believes the FMA pipe has
+// room; IMAD.WIDE issues at ~0.38 of the IMAD rate on sm_100 (profiles/INT64_PEAKS_r02.json), and the multiply-based hashes
+// are bound by exactly that pipe.
+__device__ __forceinline__ uint64_t rotl64_shf(uint64_t x, int r)
+{
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if (r == 32) return ((uint64_t)lo << 32) | hi;
+    if (r < 32) return ((uint64_t)__funnelshift_l(lo, hi, r) << 32) | __funnelshift_l(hi, lo, r);
+    return ((uint64_t)__funnelshift_l(hi, lo, r - 32) << 32) | __funnelshift_l(lo, hi, r - 32);
+}
+// a * c + acc on 64 bits, c a compile-time constant, as exactly one IMAD.WIDE and two dependent IMADs (4 slots of the
+// fmaheavy pipe): ptxas left alone computes the two cross products next to the wide one and adds them with a separate
+// IMAD.IADD — shorter latency, but one more instruction on the pipe that bounds the multiply-based hashes.
+__device__ __forceinline__ uint64_t mad64c(uint64_t a, uint64_t c, uint64_t acc)
+{
+#ifndef __CUDACC__
+    return a * c + acc;   // host build of the device hashers (tests/emul): same value, no PTX
+#else
+    const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32), clo = (uint32_t)c, chi = (uint32_t)(c >> 32);
+    uint32_t lo, hi;
+    asm("{\n\t"
+        ".reg .u64 w;\n\t"
+        "mad.wide.u32 w, %2, %4, %6;\n\t"
+        "mov.b64 {%0, %1}, w;\n\t"
+        "mad.lo.u32 %1, %3, %4, %1;\n\t"
+        "mad.lo.u32 %1, %2, %5, %1;\n\t"
+        "}"
+        : "=r"(lo), "=&r"(hi)
+        : "r"(alo), "r"(ahi), "r"(clo), "r"(chi), "l"(acc));
+    return ((uint64_t)hi << 32) | lo;
+#endif
+}
+__device__ __forceinline__ uint64_t mul64c(uint64_t a, uint64_t c) { return mad64c(a, c, 0); }
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 __device__ __forceinline__ uint64_t bswap64(uint64_t x)
 {
@@ -34,6 +68,10 @@ __device__ __forceinline__ uint64_t mulfold64(uint64_t a, uint64_t b) { return (
 // 64 lanes/clk/SM) is idle in the integer hashes, so moving adds there shortens the ALU-bound kernels.
 static __constant__ uint32_t c_one = 1u;
 __device__ __forceinline__ uint32_t fma_add(uint32_t x, uint32_t y) { return x * c_one + y; }
+// ... and the other way round for the kernels bound by the FMA pipe (the 64-bit multiplies of the multiply-based hashes): a
+// three-input add can only be an IADD3, which lives on the ALU pipe; ptxas left alone issues 2-input adds as IMAD.IADD / VIADD.
+static __constant__ uint32_t c_zero = 0u;
+__device__ __forceinline__ uint32_t alu_add(uint32_t x, uint32_t y) { return x + y + c_zero; }
 
 // ASCII upper-casing of 4 packed bytes (a-z -> A-Z, everything else untouched, bytes >= 0x80 too).
 // FMA: the two adds as IMADs on the FMA pipe — every kernel that upper-cases while hashing is bound by the ALU pipe
@@ -45,6 +83,14 @@ __device__ __forceinline__ uint32_t upper4(uint32_t x)
     uint32_t y = x & 0x7f7f7f7fu;
     uint32_t ge_a = FMA ? fma_add(y, 0x1f1f1f1fu) : y + 0x1f1f1f1fu;   // bit7 set  <=>  (b & 0x7f) >= 'a'
     uint32_t gt_z = FMA ? fma_add(y, 0x05050505u) : y + 0x05050505u;   // bit7 set  <=>  (b & 0x7f) >  'z'
+    uint32_t m = ge_a & ~gt_z & ~x & 0x80808080u;
+    return x ^ (m >> 2);
+}
+// the same with both adds pinned to the ALU pipe (alu_add)
+__device__ __forceinline__ uint32_t upper4_alu(uint32_t x)
+{
+    uint32_t y = x & 0x7f7f7f7fu;
+    uint32_t ge_a = alu_add(y, 0x1f1f1f1fu), gt_z = alu_add(y, 0x05050505u);
     uint32_t m = ge_a & ~gt_z & ~x & 0x80808080u;
     return x ^ (m >> 2);
 }

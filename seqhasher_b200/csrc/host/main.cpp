@@ -191,7 +191,7 @@ struct Slot {
     int rc = 0;
     std::string err;
     std::vector<uint8_t> acc;   // output of all passes but the last
-    size_t consumed = 0, n_empty = 0;
+    size_t consumed = 0, n_empty = 0, n_nonascii = 0;
     long long ready = -1, done = -1, freed = -1;   // chunk sequence numbers
     bool quit = false;
     std::mutex mu;
@@ -219,6 +219,7 @@ void slot_worker(Slot *s, const RunArgs *a)
         }
         s->acc.clear();
         s->n_empty = 0;
+        s->n_nonascii = 0;
         s->err.clear();
         size_t off = 0, n = s->n_bytes;
         int rc = 0;
@@ -227,6 +228,7 @@ void slot_worker(Slot *s, const RunArgs *a)
                                   (int)a->ids.size(), a->flags, a->headers_only, a->label);
             if (rc < 0) { s->err = shb_last_error(); break; }
             s->n_empty += shb_textproc_empty_records(s->tp);
+            s->n_nonascii += shb_textproc_nonascii(s->tp);
             const size_t used = shb_textproc_consumed(s->tp);
             off += used;
             // more records than the index holds: the rest of a whole chunk goes through again
@@ -298,6 +300,7 @@ int process_sequences(host::Source &in, FILE *out, const Config &cfg, int n_gpus
     long long submitted = -1;        // last chunk sequence handed to a slot
     bool reader_done = false;
     int rc = 0;                      // first failure, in chunk order
+    const bool allow_nonascii = getenv("SHB_ALLOW_NONASCII") != nullptr;
     std::atomic<bool> failed{false};
     std::thread writer([&] {
         for (long long seq = 0;; seq++) {
@@ -314,6 +317,13 @@ int process_sequences(host::Source &in, FILE *out, const Config &cfg, int n_gpus
             if (rc == 0) {
                 if (s.rc < 0) {
                     err = "Error reading record: " + s.err;
+                    rc = 1;
+                } else if (s.n_nonascii && !allow_nonascii) {
+                    // seqhasher.go:243-251: for such records the reference's strip / upper-casing follow Unicode rules; this
+                    // engine is byte-wise ASCII, so its digests could differ: refuse instead (README.md:259 of the reference
+                    // declares non-ASCII input unsupported)
+                    err = "Error reading record: non-ASCII bytes in sequence data are not supported "
+                          "(set SHB_ALLOW_NONASCII=1 to hash them as plain bytes)";
                     rc = 1;
                 } else {
                     size_t nout = 0;

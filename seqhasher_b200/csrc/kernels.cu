@@ -594,6 +594,37 @@ __global__ void synth_fill_kernel(uint8_t *__restrict__ res, size_t total, uint6
     }
 }
 
+// bytes >= 0x80 in res[0, total): SHB_FLAG_CHECK_ASCII (the caller cannot vouch for ASCII input; seqhasher.go:243-251)
+__global__ void __launch_bounds__(256) count_nonascii_kernel(const uint8_t *__restrict__ res, size_t total, unsigned long long *__restrict__ count)
+{
+    const size_t units = (total + 15) >> 4;   // the buffer is readable (zero padded) to the next 16 bytes
+    uint32_t c = 0;
+    for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(res) + u);
+        uint32_t m[4] = {v.x & 0x80808080u, v.y & 0x80808080u, v.z & 0x80808080u, v.w & 0x80808080u};
+        if (16 * u + 16 > total) {            // the last unit: bytes past the end do not count
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const long long valid = (long long)total - (long long)(16 * u + 4 * k);
+                if (valid <= 0) m[k] = 0;
+                else if (valid < 4) m[k] &= (1u << (8 * valid)) - 1u;
+            }
+        }
+        c += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(count, (unsigned long long)c);
+}
+
+cudaError_t launch_count_nonascii(const uint8_t *res, size_t total_bytes, unsigned long long *count, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess || total_bytes == 0) return e;
+    count_nonascii_kernel<<<148 * 8, 256, 0, st>>>(res, total_bytes, count);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_synth_fill(uint8_t *res, size_t total_bytes, uint64_t seed, unsigned lower_permille,
                               unsigned n_permille, cudaStream_t st)
 {
@@ -611,6 +642,8 @@ cudaError_t launch_synth_fill(uint8_t *res, size_t total_bytes, uint64_t seed, u
 #define PROBE_OP_SHF(x, y) asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(x) : "r"(y))
 #define PROBE_OP_IMAD(x, y, z) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(y), "r"(z))
 #define PROBE_OP_PRMT(x, y) asm volatile("prmt.b32 %0, %0, %1, 0x2103;" : "+r"(x) : "r"(y))
+#define PROBE_OP_ADDI(x) asm volatile("add.u32 %0, %0, 0x1f1f1f1f;" : "+r"(x))
+#define PROBE_OP_ADD2(x, y) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(y))
 
 template <int KIND>
 __global__ void __launch_bounds__(256) probe_kernel(int iters, uint32_t *sink)
@@ -638,6 +671,30 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, uint32_t *sink)
                 } else if (KIND == 6) {
                     if (u & 1) PROBE_OP_IMAD(c[k], y, z);
                     else PROBE_OP_LOP3(c[k], y, z);
+                } else if (KIND == 32) {          // add with an immediate: ptxas emits VIADD — which pipe takes it?
+                    PROBE_OP_ADDI(c[k]);
+                } else if (KIND == 33) {          // VIADD : IMAD 1:1
+                    if (u & 1) PROBE_OP_IMAD(c[k], y, z);
+                    else PROBE_OP_ADDI(c[k]);
+                } else if (KIND == 34) {          // VIADD : LOP3 1:1
+                    if (u & 1) PROBE_OP_LOP3(c[k], y, z);
+                    else PROBE_OP_ADDI(c[k]);
+                } else if (KIND == 35) {          // two-input register add (IADD3 / IMAD.IADD: ptxas' choice) : IMAD 1:1
+                    if (u & 1) PROBE_OP_IMAD(c[k], y, z);
+                    else PROBE_OP_ADD2(c[k], y);
+                } else if (KIND == 36) {          // two-input register add : LOP3 1:1
+                    if (u & 1) PROBE_OP_LOP3(c[k], y, z);
+                    else PROBE_OP_ADD2(c[k], y);
+                } else if (KIND == 37) {          // LOP3 : IMAD 2:1
+                    if (u % 3 == 2) PROBE_OP_IMAD(c[k], y, z);
+                    else PROBE_OP_LOP3(c[k], y, z);
+                } else if (KIND == 39) {          // LOP3 : add-imm : IMAD : add-imm
+                    if ((u & 3) == 0) PROBE_OP_LOP3(c[k], y, z);
+                    else if ((u & 3) == 2) PROBE_OP_IMAD(c[k], y, z);
+                    else PROBE_OP_ADDI(c[k]);
+                } else if (KIND == 38) {          // LOP3 : IMAD 1:2
+                    if (u % 3 == 2) PROBE_OP_LOP3(c[k], y, z);
+                    else PROBE_OP_IMAD(c[k], y, z);
                 }
             }
         }
@@ -646,6 +703,45 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, uint32_t *sink)
 #pragma unroll
     for (int k = 0; k < 8; k++) acc ^= c[k];
     if (acc == 0x12345u) sink[0] = acc;   // practically never true; keeps the chains alive
+}
+
+// kinds 8..13: the 64-bit building blocks of the multiply-based hashes, 8 independent 64-bit chains per thread, 64 ops per
+// chain per iteration, counted as ONE op each:  8 mad.wide.u32 (IMAD.WIDE.U32)   9 mad.hi.u32 (IMAD.HI.U32)
+// 10 c = c * y + z on 64 bits (mul64: what xxh64 / murmur3 rounds are made of)   11 c = fold(c * y) (128-bit product, xxh3 /
+// rapidhash)   12 64-bit rotate   13 64-bit add
+template <int KIND>
+__global__ void __launch_bounds__(256) probe64_kernel(int iters, uint32_t *sink)
+{
+    uint64_t c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = ((uint64_t)(threadIdx.x * 2654435761u + k * 40503u + blockIdx.x) << 32) | (threadIdx.x * 40503u + k);
+    const uint64_t y = c[0] | 1u, z = c[1] | 3u;
+    const uint32_t y32 = (uint32_t)y;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 64; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (KIND == 8) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[k]) : "r"((uint32_t)c[k]), "r"(y32));
+                else if (KIND == 9) {
+                    uint32_t lo = (uint32_t)c[k];
+                    asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(lo) : "r"(y32), "r"((uint32_t)z));
+                    c[k] = (c[k] & 0xffffffff00000000ull) | lo;
+                } else if (KIND == 10) c[k] = c[k] * y + z;
+                else if (KIND == 11) c[k] = (c[k] * y) ^ __umul64hi(c[k], y);
+                else if (KIND == 12) c[k] = (c[k] << 31) | (c[k] >> 33);
+                else if (KIND == 13) c[k] = c[k] + y;
+            }
+            if (KIND == 12 || KIND == 13) {   // keep the compiler from collapsing the chain
+#pragma unroll
+                for (int k = 0; k < 8; k++) asm volatile("" : "+l"(c[k]));
+            }
+        }
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc ^= c[k];
+    if (acc == 0x12345u) sink[0] = (uint32_t)acc;
 }
 
 // kinds 16..31: the real SHA-1 compression on register data, pipe-balancing variant = kind - 16
@@ -684,6 +780,20 @@ cudaError_t launch_probe(int kind, int iters, uint32_t *sink, double *lane_instr
     case 4: probe_kernel<4><<<blocks, 256, 0, st>>>(iters, sink); break;
     case 5: probe_kernel<5><<<blocks, 256, 0, st>>>(iters, sink); break;
     case 6: probe_kernel<6><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 32: probe_kernel<32><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 33: probe_kernel<33><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 34: probe_kernel<34><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 35: probe_kernel<35><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 36: probe_kernel<36><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 37: probe_kernel<37><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 38: probe_kernel<38><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 39: probe_kernel<39><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 8: probe64_kernel<8><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 9: probe64_kernel<9><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 10: probe64_kernel<10><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 11: probe64_kernel<11><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 12: probe64_kernel<12><<<blocks, 256, 0, st>>>(iters, sink); break;
+    case 13: probe64_kernel<13><<<blocks, 256, 0, st>>>(iters, sink); break;
     case 7: case 16: launch_probe_sha1<0>(iters, sink, st); break;
     case 17: launch_probe_sha1<1>(iters, sink, st); break;
     case 18: launch_probe_sha1<2>(iters, sink, st); break;
@@ -706,7 +816,7 @@ cudaError_t launch_probe(int kind, int iters, uint32_t *sink, double *lane_instr
     default: return cudaErrorInvalidValue;
     }
     g_launches++;
-    if (kind == 7 || kind >= 16) *lane_instr = 148.0 * 16 * 128 * (double)iters * 613.0;
+    if (kind == 7 || (kind >= 16 && kind < 32) || kind == 40 || kind == 56 || kind == 72) *lane_instr = 148.0 * 16 * 128 * (double)iters * 613.0;
     else *lane_instr = (double)blocks * 256.0 * (double)iters * 64.0 * 8.0 * (kind == 1 ? 1.0 : 1.0);
     return cudaGetLastError();
 }

@@ -69,6 +69,9 @@ cudaError_t launch_normalise(const uint8_t *res, const int64_t *offs, size_t n, 
 size_t scan_tmp_bytes(size_t n);
 cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, void *tmp, cudaStream_t st);
 
+// bytes >= 0x80 in res[0, total_bytes) into *count (device memory)
+cudaError_t launch_count_nonascii(const uint8_t *res, size_t total_bytes, unsigned long long *count, cudaStream_t st);
+
 cudaError_t launch_lengths(const int64_t *offs, size_t n, int64_t *out_len, cudaStream_t st);
 
 cudaError_t launch_synth_fill(uint8_t *res, size_t total_bytes, uint64_t seed, unsigned lower_permille,

@@ -14,6 +14,18 @@
 
 namespace shb {
 
+// Grid of a persistent (grid-stride) kernel: exactly the CTAs that are resident at once.  Registers and shared memory decide
+// how many fit per SM; one CTA more than fit would run as a second, nearly empty wave after the others have done their share.
+template <class K>
+static int resident_ctas(K kernel, int threads)
+{
+    int occ = 0, sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0);
+    return (occ > 0 ? occ : 4) * (sms > 0 ? sms : 148);
+}
+
 // ------------------------------------------------------------------------------------------- ntHash
 
 __device__ __forceinline__ uint64_t rotl64v(uint64_t x, uint32_t r)   // r in 0..63, run-time
@@ -32,13 +44,52 @@ __device__ __forceinline__ uint32_t valid_mask4(int64_t pos, int64_t len)
     return m;
 }
 
+// Warp per record.  A lane folds whole 16-byte units (one coalesced LDG.128 each): byte j of a unit looks up table
+// 15 - j of sixteen pre-rotated copies of the seed table (32 KiB of shared memory per CTA), so a unit is 16 look-ups XORed
+// together with no rotation at all; the units of one lane lie 512 bytes apart, i.e. they all carry the same rotation
+// (512 = 0 mod 64), which is applied once per lane before the warp's XOR reduction.  Four units are in flight per lane.
+// Bound: the 8 bytes every look-up returns per lane — shared memory delivers 128 B per clock and SM, two wavefronts per
+// LDS.64 — not HBM and not the ALU.
+__device__ __forceinline__ uint4 ldg16_issue(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+#ifndef NT_MIN_BLOCKS
+#define NT_MIN_BLOCKS 4   // 64 registers: room for four 128-bit loads in flight per lane (A/B: profiles/r02_nthash_variants.txt)
+#endif
+constexpr uint32_t NT16_WORDS = 16 * 256;   // uint64 entries: [rotation 0..15][byte]
+
 template <bool UPPER>
-__global__ void __launch_bounds__(256) nthash_warp_kernel(const uint8_t *__restrict__ res,
+__device__ __forceinline__ uint64_t nt_unit16(uint4 v, const uint64_t *lut)
+{
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint64_t t = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t x = UPPER ? upper4(w[k]) : w[k];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b = __byte_perm(x, 0, 0x4440 | j);             // byte j, zero-extended (one PRMT)
+            t ^= lut[(15 - (4 * k + j)) * 256 + b];
+        }
+    }
+    return t;
+}
+
+template <bool UPPER>
+__global__ void __launch_bounds__(256, NT_MIN_BLOCKS) nthash_warp_kernel(const uint8_t *__restrict__ res,
                                                           const int64_t *__restrict__ offs, size_t n,
                                                           uint8_t *__restrict__ out)
 {
-    __shared__ uint64_t lut[NT_LUT_WORDS];   // pre-rotated seed look-ups, hash_fast.cuh
-    nt_fill_lut<false>(lut);   // long reads: no index swizzle (it costs 3 % here; uppercase data has nothing to separate)
+    __shared__ uint64_t lut[NT16_WORDS];
+    for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) {
+        const uint64_t s = g_nt_seed_table.v[c];
+#pragma unroll
+        for (int r = 0; r < 16; r++) lut[r * 256 + c] = r ? rotl64(s, r) : s;
+    }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -50,25 +101,40 @@ __global__ void __launch_bounds__(256) nthash_warp_kernel(const uint8_t *__restr
             if (lane == 0) *reinterpret_cast<uint2 *>(o) = make_uint2(0u, 0u);
             continue;
         }
-        // 16-byte units of the aligned window that covers the record
+        // 16-byte units of the aligned window that covers the record; unit u holds record bytes [16 u - head, 16 u - head + 16)
         const int64_t a0 = s & ~(int64_t)15;
-        const int64_t nunits = (e - a0 + 15) >> 4;
+        const uint32_t head = (uint32_t)(s - a0);
+        const uint32_t nunits = (uint32_t)((e - a0 + 15) >> 4);           // record < 2^31 bytes
+        const uint4 *base = reinterpret_cast<const uint4 *>(res + a0);
         uint64_t acc = 0;
-        for (int64_t u = lane; u < nunits; u += 32) {
-            const int64_t pos = a0 + 16 * u - s;   // record position of the unit's first byte (may be < 0)
-            uint4 v = __ldg(reinterpret_cast<const uint4 *>(res + a0) + u);
-            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            const bool interior = pos >= 0 && pos + 16 <= len;
-            if (!interior) {   // bytes outside the record contribute nothing: map them to 0 (seed 0)
+        // interior units: 1 .. nunits - 2 (the first and the last may hold bytes of the neighbours)
+        uint32_t u = lane;
+        if (u == 0) u = 32;                                               // lane 0 takes unit 0 separately below
+        const uint32_t last = nunits - 1;
+        for (; u + 96 < last; u += 128) {
+            // four loads issued back to back (volatile: ptxas otherwise sinks the third and fourth below the first units' work)
+            const uint4 v0 = ldg16_issue(base + u), v1 = ldg16_issue(base + u + 32), v2 = ldg16_issue(base + u + 64), v3 = ldg16_issue(base + u + 96);
+            acc ^= nt_unit16<UPPER>(v0, lut) ^ nt_unit16<UPPER>(v1, lut);
+            acc ^= nt_unit16<UPPER>(v2, lut) ^ nt_unit16<UPPER>(v3, lut);
+        }
+        for (; u < last; u += 32) acc ^= nt_unit16<UPPER>(__ldg(base + u), lut);
+        // edge units: bytes outside the record become 0, whose seed is 0
+        if (lane == 0 || (last % 32u == lane && last != 0)) {
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                const uint32_t eu = pass == 0 ? 0u : last;
+                if (pass == 0 ? lane != 0 : (last == 0 || last % 32u != lane)) continue;
+                uint4 v = __ldg(base + eu);
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                const int64_t pos = (int64_t)16 * eu - head;
 #pragma unroll
                 for (int k = 0; k < 4; k++) w[k] &= valid_mask4(pos + 4 * k, len);
+                acc ^= nt_unit16<UPPER>(make_uint4(w[0], w[1], w[2], w[3]), lut);
             }
-            uint64_t t = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) t = nt_fold4<false>(t, UPPER ? upper4(w[k]) : w[k], lut);
-            // t = XOR_j rol(seed[b_j], 15 - j); position pos+j carries rotation (len-1-pos-j) mod 64
-            acc ^= rotl64v(t, (uint32_t)((len - 16 - pos) & 63));
         }
+        // byte j of unit u sits at record position p = 16 u - head + j and carries rotation (len - 1 - p) mod 64; the table gave
+        // it 15 - j, so the unit still owes (len - 16 - 16 u + head) mod 64 — the same for every unit of this lane
+        acc = rotl64v(acc, (uint32_t)((len - 16 + head - 16 * (int64_t)lane) & 63));
 #pragma unroll
         for (int d = 16; d; d >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, d);
         if (lane == 0) store_be64(o, acc);
@@ -79,8 +145,10 @@ cudaError_t launch_nthash_long(bool upper, const uint8_t *res, const int64_t *of
                                cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    static int per_sm[2] = {0, 0};
+    if (!per_sm[upper]) per_sm[upper] = upper ? resident_ctas(nthash_warp_kernel<true>, 256) : resident_ctas(nthash_warp_kernel<false>, 256);
     size_t blocks = (n + 7) / 8;   // 8 warps per CTA
-    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    if (blocks > (size_t)per_sm[upper]) blocks = (size_t)per_sm[upper];
     if (upper) nthash_warp_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(res, offs, n, out);
     else nthash_warp_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(res, offs, n, out);
     g_launches++;
@@ -210,8 +278,10 @@ __global__ void __launch_bounds__(256) xxh3_warp_kernel(const uint8_t *__restric
 cudaError_t launch_xxh3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, uint8_t *out, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    static int per_sm[2] = {0, 0};
+    if (!per_sm[upper]) per_sm[upper] = upper ? resident_ctas(xxh3_warp_kernel<true>, 256) : resident_ctas(xxh3_warp_kernel<false>, 256);
     size_t blocks = (n + 7) / 8;
-    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    if (blocks > (size_t)per_sm[upper]) blocks = (size_t)per_sm[upper];
     if (upper) xxh3_warp_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(res, offs, n, out);
     else xxh3_warp_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(res, offs, n, out);
     g_launches++;

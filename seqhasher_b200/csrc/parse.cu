@@ -243,6 +243,19 @@ __global__ void __launch_bounds__(FX_THREADS) fx_emit_kernel(const uint8_t *__re
             m &= m - 1;
         }
     }
+    if (!COUNT) {
+        // Sequence bytes >= 0x80: Go's bytes.Fields / bytes.ToUpper switch to Unicode rules for a record that holds one
+        // (seqhasher.go:243-251), this engine is byte-wise ASCII.  They are counted so that the host can refuse the input
+        // instead of printing digests that differ from the reference's.
+        uint32_t hi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) hi |= ((((w[k] & 0x80808080u) >> 7) * 0x00204081u) >> 21 & 0xfu) << (4 * k);
+        hi &= kept_mask;
+        if (__any_sync(0xffffffffu, hi != 0)) {
+            const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(hi));
+            if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&info->n_nonascii), (unsigned long long)c);
+        }
+    }
     const uint32_t my_kept = __popc(kept_mask), my_ev = __popc(ev_mask);
     uint32_t inc_k = my_kept, inc_e = my_ev;
     for (int d = 1; d < 32; d <<= 1) {

@@ -22,6 +22,7 @@ struct FxInfo {            // device-side result block
     long long n_empty;     // records whose sequence is empty (formatter)
     long long reserved;
     long long first_bad;   // index of the first malformed record (LLONG_MAX: none); set by the splitter
+    long long n_nonascii;  // sequence bytes >= 0x80 in the chunk (the reference normalises those with Unicode rules, seqhasher.go:243-251)
 };
 
 struct FxOut {

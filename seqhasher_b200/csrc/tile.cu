@@ -12,6 +12,7 @@
 // re-reads the record per hash, seqhasher.go:255-259).  Tiles that do not fit the shared-memory
 // budget fall back, per CTA, to direct global reads, so any input is still handled.
 #include "hash_all.cuh"
+#include "hash_fused3.cuh"
 
 namespace shb {
 
@@ -82,6 +83,9 @@ __device__ __forceinline__ uint32_t strip_to_scratch(const uint8_t *__restrict__
 }
 
 constexpr uint32_t bit(int a) { return 1u << a; }
+constexpr uint32_t FAST_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_CITYHASH) | bit(A_MURMUR3) | bit(A_NTHASH) |
+                               bit(A_RAPIDHASH) | bit(A_RAPIDHASH32);
+constexpr uint32_t C3_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_MURMUR3);
 
 // STRIP fuses the whitespace strip (seqhasher.go:246) into the tile pass without a second look at the data:
 // the readers OR a "byte < 0x21" test into a flag while the record is being hashed (for a fused set with
@@ -94,7 +98,10 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
                                                         int64_t *__restrict__ out_len)
 {
     constexpr bool MULTI = (MASK & (MASK - 1)) != 0;
-    constexpr bool INPLACE = MULTI && UPPER;          // tile upper-cased in place by a cooperative pass
+    // xxhash + xxh3 + murmur3 (config C3): one fused pass per record that loads, aligns and upper-cases every 16 bytes
+    // once in registers for the three hashes (hash_fused3.cuh), so no in-place upper-casing pass either
+    constexpr bool FUSED3 = MASK == C3_MASK;
+    constexpr bool INPLACE = MULTI && UPPER && !FUSED3;   // tile upper-cased in place by a cooperative pass
     constexpr bool SPECULATE = STRIP && !INPLACE;     // whitespace candidates detected by the readers
     // The CTA hands its 128 records to the threads longest first, so that a warp's 32 records finish together
     // (amplicon reads of 100-600 bp otherwise run every warp for its longest record: x1.3-1.6 for the INT-bound
@@ -197,9 +204,22 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
             // thread that reads them, makes them letters first.
             if (SPECULATE && i + 1 == r1) *reinterpret_cast<uint2 *>(tile + bytes) = make_uint2(0x41414141u, 0x41414141u);
             for (int pass = 0;; pass++) {
-                SmemReader<UPPER && !MULTI, SPECULATE, FMA_PREP> r(tile, start);
-                hash_set<MASK, !UPPER>(r, len, i, out, rmask, NT ? s_nt : nullptr);
-                if (!SPECULATE || pass == 1 || !r.saw_ws_candidate()) break;
+                bool cand;
+                if (FUSED3 && len >= 17u && len <= 240u) {
+                    Fused3Out fo;
+                    const uint32_t wsf = fused3_record<UPPER, SPECULATE>(tile, start, len, fo);
+                    store_be64(out.p[A_XXHASH] + i * 8, fo.xxh64);
+                    store_be64(out.p[A_XXH3] + i * 8, fo.xxh3);
+                    uint8_t *om = out.p[A_MURMUR3] + i * 16;
+                    store_be64(om, fo.m1);
+                    store_be64(om + 8, fo.m2);
+                    cand = SPECULATE && (wsf & 0x80808080u) != 0;
+                } else {
+                    SmemReader<UPPER && !INPLACE, SPECULATE, FMA_PREP> r(tile, start);
+                    hash_set<MASK, !UPPER>(r, len, i, out, rmask, NT ? s_nt : nullptr);
+                    cand = r.saw_ws_candidate();
+                }
+                if (!SPECULATE || pass == 1 || !cand) break;
                 len = strip_in_smem(tile, start, len);   // rare: compact this record, hash it again
             }
             if (STRIP && out_len) out_len[i] = len;
@@ -216,10 +236,6 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
         }
     }
 }
-
-constexpr uint32_t FAST_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_CITYHASH) | bit(A_MURMUR3) | bit(A_NTHASH) |
-                               bit(A_RAPIDHASH) | bit(A_RAPIDHASH32);
-constexpr uint32_t C3_MASK = bit(A_XXHASH) | bit(A_XXH3) | bit(A_MURMUR3);
 
 template <uint32_t MASK, bool UPPER, bool STRIP>
 static cudaError_t launch_tile_k(const uint8_t *res, const int64_t *offs, size_t n, const OutPtrs &out, uint32_t rmask,

@@ -3,10 +3,15 @@ Header layout, --headersonly and FASTA/FASTQ formatting follow seqhasher.go:261-
 from __future__ import annotations
 
 import io
+import os
 
 from .fastx import FastxError, read_records
 from .hasher import GpuHasher, shared_hasher
 
+# seqhasher.go:243-251: a record with a byte >= 0x80 is normalised with Unicode rules by the reference (UTF-8 decoding, Unicode
+# spaces, rune-wise upper-casing with U+FFFD for invalid bytes); this engine is byte-wise ASCII, so it refuses such input rather
+# than print digests that may differ (the reference's README.md:259 declares non-ASCII input unsupported)
+ERR_NONASCII = "non-ASCII bytes in sequence data are not supported (set SHB_ALLOW_NONASCII=1 to hash them as plain bytes)"
 BATCH_RECORDS = 1 << 18
 BATCH_BYTES = 48 << 20
 
@@ -55,6 +60,9 @@ def process_sequences(input_stream, output_stream, cfg, hasher: GpuHasher | None
                     raise RuntimeError(f"Failed to create reader: {e}") from None
                 raise RuntimeError(f"Error reading record: {e}") from None
             first = False
+            if not rec.seq.isascii() and not os.environ.get("SHB_ALLOW_NONASCII"):
+                flush(batch)
+                raise RuntimeError(f"Error reading record: {ERR_NONASCII}")
             batch.append(rec)
             nbytes += len(rec.seq)
             if len(batch) >= BATCH_RECORDS or nbytes >= BATCH_BYTES:
@@ -157,6 +165,8 @@ def process_sequences_gpu(input_stream, output_stream, cfg, textproc=None, chunk
                                                      None if no_file_name else label.encode())
             except B.SeqhashError as e:
                 raise fail_read(ERR_INVALID if ERR_INVALID in str(e) else e) from None
+            if tp.nonascii and not os.environ.get("SHB_ALLOW_NONASCII"):
+                raise fail_read(ERR_NONASCII)
             for _ in range(nempty * len(ids)):
                 print(EMPTY_MSG, file=log)
             output_stream.write(memoryview(out))

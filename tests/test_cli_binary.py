@@ -251,3 +251,13 @@ def test_binary_open_errors_use_the_errno_text(tmp_path):
     assert rc == 1 and err.startswith("Error opening output: open ") and err.strip().endswith("no such file or directory")
     rc, _, err = run(["test.fasta", str(d)])
     assert rc == 1 and err.strip().endswith("is a directory")
+
+
+@pytest.mark.gpu
+def test_binary_refuses_nonascii_sequence_bytes():
+    data = b">ok\nACGT\n>bad\nAC\xc3\xa9GT\n"
+    rc, out, err = run_env(["--nofilename", "--headersonly", "-", "-"], {}, stdin=data)
+    assert rc == 1 and "non-ASCII bytes in sequence data are not supported" in err
+    rc, out, err = run_env(["--nofilename", "--headersonly", "-", "-"], {"SHB_ALLOW_NONASCII": "1"}, stdin=data)
+    import hashlib
+    assert rc == 0 and out == (hashlib.sha1(b"ACGT").hexdigest() + ";ok\n" + hashlib.sha1(b"AC\xc3\xa9GT").hexdigest() + ";bad\n").encode()

@@ -1,0 +1,58 @@
+"""Device hashers compiled for the HOST (tests/emul/cuda_runtime.h stands in for the CUDA headers) and checked
+against the oracle: the arithmetic of the fused xxhash + xxh3 + murmur3 pass (csrc/hash_fused3.cuh) is verified
+on every length and alignment without a GPU; the -m gpu tests then only have to show that the kernel around it
+feeds it the right bytes.  Test infrastructure only: the product has no CPU path."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "emul", "_build", "libfused3_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    src = os.path.join(HERE, "emul", "fused3_emul.cpp")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-I" + os.path.join(HERE, "emul"),
+                    "-I" + os.path.join(ROOT, "seqhasher_b200", "csrc"), "-o", SO, src], check=True)
+    L = ctypes.CDLL(SO)
+    L.emul_fused3.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.emul_fused3.restype = ctypes.c_uint32
+    return L
+
+
+def _check(emul, oracle, buf, start, n, upper):
+    out = (ctypes.c_uint64 * 4)()
+    flag = emul.emul_fused3(buf.ctypes.data, start, n, upper, 1, out)
+    rec = buf[start:start + n].tobytes()
+    data = rec.upper() if upper else rec
+    want = [oracle.get_hash_func(a)(data) for a in ("xxhash", "xxh3", "murmur3")]
+    got = ["%016x" % out[0], "%016x" % out[1], "%016x%016x" % (out[2], out[3])]
+    assert got == want, (n, start, upper)
+    assert bool(flag) == any(c < 0x21 for c in rec), (n, start, upper, "whitespace flag")
+
+
+def test_fused3_every_length_and_alignment(emul, oracle):
+    rng = np.random.default_rng(0)
+    for n in range(17, 241):
+        for start in (0, 1, 2, 3, 5, 18):
+            buf = rng.choice(np.frombuffer(b"ACGTacgtNn", dtype=np.uint8), size=start + n + 64).astype(np.uint8)
+            buf[start + n:] = rng.integers(0, 256, size=64)        # bytes past the record: anything, whitespace included
+            _check(emul, oracle, buf, start, n, 1)
+            _check(emul, oracle, buf, start, n, 0)
+
+
+def test_fused3_arbitrary_bytes_and_whitespace_flag(emul, oracle):
+    rng = np.random.default_rng(1)
+    for trial in range(1500):
+        n, start = int(rng.integers(17, 241)), int(rng.integers(0, 64))
+        buf = rng.integers(0x21, 256, size=start + n + 64).astype(np.uint8)
+        if trial % 3 == 0:                                           # one whitespace byte somewhere inside the record
+            buf[start + int(rng.integers(0, n))] = int(rng.choice([9, 10, 11, 12, 13, 32]))
+        buf[start + n:] = rng.integers(0, 0x21, size=64)             # everything past the end looks like whitespace
+        _check(emul, oracle, buf, start, n, int(trial & 1))

@@ -1,5 +1,5 @@
 """The whole record loop on the GPU (shb_textproc: split -> strip -> upper -> hash -> header rewrite -> format)
-against a CPU expectation built from the host reader (bio semantics) + the oracle, on the reference's fixtures
+against a CPU expectation built from the oracle's reader restatement (oracle/reader.py) + the oracle hashes, on the reference's fixtures
 and on synthetic multi-line FASTA / 4-line FASTQ that span many 4 KiB scan blocks and several chunks."""
 import io
 import os
@@ -19,27 +19,13 @@ def H():
 
 
 def expected(oracle, data: bytes, cfg) -> bytes:
-    """seqhasher.go:210-286 on the CPU: host reader + oracle hashes + the reference's formatting."""
-    from seqhasher_b200.host.fastx import read_records
-    label, nofile = cfg.input_file_name, cfg.no_file_name
-    if cfg.name_override:
-        label = cfg.name_override
-    elif label == "-":
-        nofile = True
-    flags = 2 | (0 if cfg.case_sensitive else 1)
-    out = io.BytesIO()
-    for rec in read_records(io.BytesIO(data)):
-        seq = oracle.normalise(rec.seq, flags)
-        hashes = ";".join(oracle.get_hash_func(t)(seq) for t in cfg.hash_types).encode()
-        parts = ([] if nofile else [label.encode()]) + ([hashes] if cfg.hash_types else []) + [rec.name]
-        name = b";".join(parts)
-        if cfg.headers_only:
-            out.write(name + b"\n")
-        elif rec.qual:
-            out.write(b"@" + name + b"\n" + seq + b"\n+\n" + rec.qual + b"\n")
-        else:
-            out.write(b">" + name + b"\n" + seq + b"\n")
-    return out.getvalue()
+    """seqhasher.go:210-286 on the CPU, entirely from oracle/: the reader restatement (oracle/reader.py, with its table of
+    which reference test pins which rule) + the oracle hashes + the reference's formatting.  No product code."""
+    from oracle import reader
+    out, err = reader.process_sequences(data, cfg.hash_types, cfg.headers_only, cfg.no_file_name, cfg.case_sensitive,
+                                        cfg.input_file_name, cfg.name_override)
+    assert err is None, err
+    return out
 
 
 def run_gpu(H, data: bytes, cfg, chunk=1 << 20) -> bytes:
@@ -266,3 +252,49 @@ def test_truncated_fastq_is_an_error_after_the_complete_records(H, tail):
     from seqhasher_b200.host.fastx import FastxError, read_records
     with pytest.raises(FastxError):
         list(read_records(io.BytesIO(b"@r1\nACTG\n+\nIIII\n" + tail)))
+
+
+def test_nonascii_sequence_bytes_are_refused(H, monkeypatch):
+    """seqhasher.go:243-251: the reference normalises a record that holds a byte >= 0x80 with Unicode rules; this engine
+    is byte-wise ASCII, so both text paths refuse such input (records before it are still written) unless
+    SHB_ALLOW_NONASCII is set — never a silently different digest."""
+    data = b">ok\nACGT\n>bad\nAC\xc3\xa9GT\n>after\nTTTT\n"
+    cfg = H.Config(hash_types=["sha1"], no_file_name=True, headers_only=True, input_file_name="x")
+    monkeypatch.delenv("SHB_ALLOW_NONASCII", raising=False)
+    with pytest.raises(RuntimeError) as e:
+        run_gpu(H, data, cfg)
+    assert "non-ASCII bytes in sequence data" in str(e.value)
+    out = io.BytesIO()
+    with pytest.raises(RuntimeError) as e:
+        H.process_sequences(io.BytesIO(data), out, cfg)              # the host-side record loop
+    assert "non-ASCII bytes in sequence data" in str(e.value)
+    assert out.getvalue().startswith(b"2108994e17f6cca9f1e3f1c8a4e7a47c2c6d8c9b"[:0])   # records before it are flushed
+    # non-ASCII in NAMES is fine (names are copied, never normalised)
+    named = ">caf\xc3\xa9 1\nACTG\n".encode("latin-1")
+    assert run_gpu(H, named, cfg) == b"65c89f59d38cdbf90dfaf0b0a6884829df8396b0;caf\xc3\xa9 1\n"
+    monkeypatch.setenv("SHB_ALLOW_NONASCII", "1")
+    import hashlib
+    want = b"".join(hashlib.sha1(s).hexdigest().encode() + b";" + n + b"\n" for n, s in ((b"ok", b"ACGT"), (b"bad", b"AC\xc3\xa9GT"), (b"after", b"TTTT")))
+    assert run_gpu(H, data, cfg) == want                              # opaque bytes: ASCII-only upper-casing
+
+
+def test_batch_check_ascii_flag():
+    from seqhasher_b200 import binding as B
+    res = np.frombuffer(b"ACGT" * 1000 + b"AC\xffT" + b"ACGT" * 10, dtype=np.uint8)
+    offs = np.array([0, 4000, 4004, 4044], dtype=np.int64)
+    b = B.Batch(len(res), 3)
+    try:
+        b.load(res, offs)
+        b.submit(["xxh3"], B.FLAG_UPPER | B.FLAG_CHECK_ASCII)
+        b.wait()
+        assert b.nonascii() == 1
+        b.residues[4002] = ord("G")
+        b.submit(["xxh3"], B.FLAG_UPPER | B.FLAG_CHECK_ASCII)
+        b.wait()
+        assert b.nonascii() == 0
+        b.residues[4043] = 0x80                                      # the very last byte of the batch
+        b.submit(["xxh3"], B.FLAG_CHECK_ASCII)
+        b.wait()
+        assert b.nonascii() == 1
+    finally:
+        b.close()

@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--only", default="C3,C4,C5")
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--algos", default="nthash,blake3,xxh3,sha1,k12,xxhash,murmur3,cityhash,rapidhash,md5,sha3", help="C4split: which algorithms")
     a = ap.parse_args()
     B.init(1)
     hbm = 6465.2
@@ -74,7 +75,7 @@ def main():
         out.append(run("C4: 10-50 kb nanopore-like reads, blake3+nthash, case-sensitive", int(1_000_000 * a.scale),
                        (10_000, 50_000), ["blake3", "nthash"], 0, 0xC4, 0, 1, a.steps, hbm))
     if "C4split" in only:
-        for algo in ["nthash", "blake3", "xxh3", "sha1", "k12", "xxhash", "murmur3", "cityhash", "rapidhash", "md5", "sha3"]:
+        for algo in a.algos.split(","):
             out.append(run(f"C4 shape (x{a.scale}), {algo} alone", int(1_000_000 * a.scale), (10_000, 50_000), [algo], 0,
                            0xC4, 0, 1, a.steps, hbm))
     if "C5" in only:
