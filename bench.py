@@ -538,7 +538,9 @@ def main():
     def bench_c3():
         n3 = int(100_000_000 * args.scale)
         algos = ["xxhash", "xxh3", "murmur3"]
-        w = Workload(n3, 150, 0xC3, 20, 1, strong=True)
+        # C3 reads are 2 bits/base -> ACGT, i.e. upper case throughout, as sequencer FASTQ is.  (Round 1 timed
+        # this configuration on reads with 2 % lower-case and 0.1 % N bytes sprinkled in; that variant is `softmasked_2pct`.)
+        w = Workload(n3, 150, 0xC3, 0, 0, strong=True)
         ms, launches3, clk, outs = w.time(algos, B.FLAG_UPPER, scratch=False)
         nt = sum_over_ranks(w.n)
         alg = sum_over_ranks(w.total + 8 * (w.n + 1) + 32 * w.n)
@@ -551,7 +553,9 @@ def main():
                             "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
                             "algorithmic_bytes": int(alg), **({k: v for k, v in traffic_of("c3_tile").items()} if world == 1 and args.scale == 1.0 else
                                                               {"traffic": None, "traffic_measured_in_this_run": False}),
-                            "kernel": "hash_tile_kernel<xxhash|xxh3|murmur3, upper> (one fused launch)",
+                            "kernel": "hash_tile_kernel<xxhash|xxh3|murmur3, upper>: one launch, one fused pass per record (hash_fused3.cuh)",
+                            "bound_note": "HBM roofline as SURVEY.md §8d asks; the kernel is bound by the two integer pipes and the issue rate "
+                                          "(three multiply-based hashes: ~9 instructions per byte), see DESIGN.md §3.1",
                             "bytes": "residues once + 8 B offsets + 32 B digests per record"},
                "checksum": w.checksum_vs_cpu(algos, B.FLAG_UPPER, outs, 2_000_000)}
         r = w.e2e(algos, B.FLAG_UPPER, 2_500_000)
@@ -559,6 +563,14 @@ def main():
             obj["e2e"], got, nrec = r
             obj["e2e"]["matches_device_path"] = all(
                 bool((torch.from_numpy(g).reshape(-1) == o[: nrec * DSIZE[a]].cpu()).all()) for g, o, a in zip(got, outs, algos))
+        del w, outs
+        torch.cuda.empty_cache()
+        w = Workload(n3, 150, 0xC3, 20, 1, strong=True)
+        ms_s, _, _, outs = w.time(algos, B.FLAG_UPPER, scratch=False)
+        obj["softmasked_2pct"] = {"workload": "the same reads with 2 % lower-case and 0.1 % N bytes at random positions (round 1's C3 input): every "
+                                              "16-byte group then takes the upper-casing path",
+                                  "ms_per_step": ms_s, "value": nt / (ms_s * 1e-3), "frac_of_hbm": alg / (ms_s * 1e-3) / 1e9 / (hbm_peak * world),
+                                  "checksum": w.checksum_vs_cpu(algos, B.FLAG_UPPER, outs, 1_000_000)}
         return obj
 
     # ================================================================ C4 ============================================
@@ -584,7 +596,7 @@ def main():
                                     "ntHash rides on the same pass over the bytes",
                             "hbm_gbps": alg / (ms * 1e-3) / 1e9, "hbm_frac": alg / (ms * 1e-3) / 1e9 / (hbm_peak * world),
                             "traffic": None, "traffic_measured_in_this_run": False,
-                            "kernel": "b3_chunks_kernel (+ nthash fold) + b3_merge_kernel"},
+                            "kernel": "b3_chunks_kernel<NT> (BLAKE3 chunk CVs + the chunk's ntHash share in one pass) + b3_merge_kernel"},
                "parts": {
                    "blake3": {"ms_per_step": ms_b3, "int_T": ops / (ms_b3 * 1e-3) / 1e12, "frac_of_int_peak": ops / (ms_b3 * 1e-3) / (int_peak * world),
                               "hbm_frac": (tb + 40 * nt) / (ms_b3 * 1e-3) / 1e9 / (hbm_peak * world)},
@@ -672,20 +684,25 @@ def main():
             gz = b"".join(pool.map(member, range(0, len(text), step)))
         cli = os.path.join(ROOT, "seqhasher_b200", "bin", "seqhasher-b200")
         out = {"records": nrec, "text_bytes": len(text), "gzip_bytes": len(gz), "residue_bytes": int(lens.sum()),
-               "command": "seqhasher-b200 --headersonly --hash <all 12> in.fa.gz -", "host_cores": cores}
+               "command": "seqhasher-b200 --headersonly --name c5.fa --hash <all 12> c5.fa.gz -", "host_cores": cores}
         with tempfile.TemporaryDirectory() as td:
             pg, pp = os.path.join(td, "c5.fa.gz"), os.path.join(td, "c5.fa")
             open(pg, "wb").write(gz)
             open(pp, "wb").write(text)
             res = {}
+            env = dict(os.environ, SHB_TIMING="1")
             for name, path in (("gzip", pg), ("plain", pp)):
-                ts, outs_ = [], None
+                ts, outs_, ph = [], None, []
                 for _ in range(3):
                     t0 = time.perf_counter()
-                    p = subprocess.run([cli, "--headersonly", "--hash", ",".join(ALL12), path, "-"], capture_output=True, check=True)
+                    p = subprocess.run([cli, "--headersonly", "--name", "c5.fa", "--hash", ",".join(ALL12), path, "-"], capture_output=True,
+                                       check=True, env=env)
                     ts.append(time.perf_counter() - t0)
                     outs_ = p.stdout
-                res[name] = (min(ts[1:]), outs_)
+                    ph.append(" | ".join(x.replace("[timing]", "").strip() for x in p.stderr.decode().splitlines() if "[timing]" in x))
+                k = 1 + ts[1:].index(min(ts[1:]))
+                res[name] = (ts[k], outs_)
+                out[name + "_phases"] = ph[k]
             out["gzip_s"], out["plain_s"] = res["gzip"][0], res["plain"][0]
             out["value"], out["unit"] = nrec / res["gzip"][0], "seqs/s"
             out["text_gbps"] = len(text) / res["gzip"][0] / 1e9

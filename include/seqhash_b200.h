@@ -53,6 +53,7 @@ enum shb_algo {
 #define SHB_FLAG_FORCE_DIRECT 0x100u
 #define SHB_FLAG_NO_LONG_PATH 0x200u
 #define SHB_FLAG_NO_LENGTH_SORT 0x400u   /* thread-per-record kernels in input order instead of length order */
+#define SHB_FLAG_NO_FUSED_B3NT 0x800u    /* blake3 + nthash on long records as two passes instead of one */
 
 /* Error codes. */
 #define SHB_OK 0
@@ -186,6 +187,10 @@ int shb_synth_fill(int device, uint8_t *d_residues, size_t total_bytes, uint64_t
  * 16+v: the SHA-1 compression loop on register data with pipe-balancing variant v (hash_md.cuh);
  * 7 = 16.  Returns lane-instructions per second (613 per compression), or <0. */
 double shb_probe_int_peak(int device, int kind, int iters);
+/* Pinned host -> device copy rate of the calling process, GB/s (< 0 on failure): `bytes` of cudaHostAlloc memory (write-combined
+ * if asked), first touched by the calling thread, copied with plain cudaMemcpyAsync in `piece`-byte pieces for `seconds`.  The
+ * roof of the end-to-end numbers; tools/h2d_roof.py runs it from one process per GPU at once. */
+double shb_probe_h2d(int device, size_t bytes, size_t piece, double seconds, int write_combined);
 /* XOR checksum of the final states of the last SHA-1 probe (every variant must give the same value). */
 unsigned shb_probe_last_checksum(void);
 

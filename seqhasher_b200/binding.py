@@ -24,6 +24,7 @@ FLAG_CHECK_ASCII = 8
 FLAG_FORCE_DIRECT = 0x100
 FLAG_NO_LONG_PATH = 0x200
 FLAG_NO_LENGTH_SORT = 0x400
+FLAG_NO_FUSED_B3NT = 0x800
 
 # every symbol include/seqhash_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -31,7 +32,7 @@ EXPORTS = [
     "shb_digest_size", "shb_batch_create", "shb_batch_create_on", "shb_batch_destroy", "shb_batch_residues",
     "shb_batch_offsets", "shb_submit", "shb_wait", "shb_digests", "shb_out_lengths", "shb_out_offsets",
     "shb_out_residues", "shb_batch_nonascii", "shb_textproc_nonascii", "shb_scratch_bytes", "shb_hash_device", "shb_launch_count", "shb_synth_fill",
-    "shb_probe_int_peak", "shb_probe_last_checksum", "shb_textproc_create", "shb_textproc_destroy",
+    "shb_probe_int_peak", "shb_probe_last_checksum", "shb_probe_h2d", "shb_textproc_create", "shb_textproc_destroy",
     "shb_textproc_input", "shb_textproc_capacity", "shb_textproc_run", "shb_textproc_output", "shb_textproc_consumed",
     "shb_textproc_records", "shb_textproc_empty_records", "shb_textproc_last_ms",
 ]
@@ -86,6 +87,7 @@ def lib() -> ctypes.CDLL:
     L.shb_synth_fill.restype = c.c_int
     L.shb_probe_int_peak.argtypes = [c.c_int, c.c_int, c.c_int]; L.shb_probe_int_peak.restype = c.c_double
     L.shb_probe_last_checksum.argtypes = []; L.shb_probe_last_checksum.restype = c.c_uint
+    L.shb_probe_h2d.argtypes = [c.c_int, c.c_size_t, c.c_size_t, c.c_double, c.c_int]; L.shb_probe_h2d.restype = c.c_double
     L.shb_textproc_create.argtypes = [c.c_int, c.c_size_t]; L.shb_textproc_create.restype = c.c_void_p
     L.shb_textproc_destroy.argtypes = [c.c_void_p]; L.shb_textproc_destroy.restype = None
     L.shb_textproc_input.argtypes = [c.c_void_p]; L.shb_textproc_input.restype = c.c_void_p
@@ -249,6 +251,11 @@ def launch_count() -> int:
 
 def probe_int_peak(kind: int, iters: int = 2000, device: int = 0) -> float:
     return lib().shb_probe_int_peak(device, kind, iters)
+
+
+def probe_h2d(device: int = 0, nbytes: int = 1 << 30, piece: int = 64 << 20, seconds: float = 2.0, write_combined: bool = False) -> float:
+    """pinned host -> device copy rate of this process in GB/s"""
+    return lib().shb_probe_h2d(device, nbytes, piece, seconds, 1 if write_combined else 0)
 
 
 def probe_last_checksum() -> int:

@@ -3,6 +3,7 @@
 // There is no CPU fallback anywhere in this file: without a usable sm_100 device every call fails.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -160,8 +161,11 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
             CU(shb::launch_length_sort(offs, n, pbuf, lowest, st));
             perm = static_cast<const uint32_t *>(pbuf);
         }
+        // blake3 and nthash together on long records: ntHash is folded into the BLAKE3 chunk pass (one read of the residues)
+        const bool b3_nt_fused = b3_long && d_scratch && (want >> SHB_BLAKE3 & 1u) && (want >> SHB_NTHASH & 1u) && !(flags & SHB_FLAG_NO_FUSED_B3NT);
         for (int a = 0; a < SHB_N_ALGOS; a++) {
             if (!(want >> a & 1u)) continue;
+            if (b3_nt_fused && a == SHB_NTHASH) continue;
             if (long_ok && a == SHB_NTHASH && mean >= nt_warp_min) {
                 CU(shb::launch_nthash_long(fused_upper, res, offs, n, slot_of[a], st));
             } else if (long_ok && a == SHB_XXH3 && mean >= xxh3_warp_min) {
@@ -173,7 +177,7 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
             } else if (b3_long && a == SHB_BLAKE3 && d_scratch) {
                 ScratchLayout L(total_bytes, n);
                 CU(shb::launch_blake3_long(fused_upper, res, offs, n, total_bytes, slot_of[a],
-                                           static_cast<uint8_t *>(d_scratch) + L.b3_off, st));
+                                           static_cast<uint8_t *>(d_scratch) + L.b3_off, b3_nt_fused ? slot_of[SHB_NTHASH] : nullptr, st));
             } else {
                 const uint32_t *order = (kSortMask >> a & 1u) ? perm : nullptr;
                 // Long records, where the global sort's scattered reads cost more than they save: every CTA sorts its own
@@ -501,6 +505,41 @@ double shb_probe_int_peak(int device, int kind, int iters)
     cudaEventDestroy(e1);
     cudaFree(sink);
     return best;
+}
+
+// Pinned host -> device copy rate of this process: cudaHostAlloc (optionally write-combined), first touch on the calling
+// thread, plain cudaMemcpyAsync in `piece`-byte copies on one stream for `seconds`.  The roof of every end-to-end number;
+// run from one process per GPU at once for the aggregate of the box (tools/h2d_roof.py).  Returns GB/s, < 0 on failure.
+double shb_probe_h2d(int device, size_t bytes, size_t piece, double seconds, int write_combined)
+{
+    if (g_ndev == 0 && shb_init(0, 0) < 0) return -1.0;
+    if (cudaSetDevice(device) != cudaSuccess || bytes == 0 || piece == 0) return -1.0;
+    uint8_t *h = nullptr, *d = nullptr;
+    cudaStream_t st = nullptr;
+    double gbps = -1.0;
+    if (cudaHostAlloc(&h, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess &&
+        cudaMalloc(&d, bytes) == cudaSuccess && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess) {
+        std::memset(h, 1, bytes);
+        auto pass = [&]() {
+            for (size_t off = 0; off < bytes; off += piece)
+                cudaMemcpyAsync(d + off, h + off, std::min(piece, bytes - off), cudaMemcpyHostToDevice, st);
+            return cudaStreamSynchronize(st) == cudaSuccess;
+        };
+        bool ok = pass();   // warm-up
+        const auto t0 = std::chrono::steady_clock::now();
+        double dt = 0;
+        size_t moved = 0;
+        while (ok && dt < seconds) {
+            ok = pass();
+            moved += bytes;
+            dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (ok && dt > 0) gbps = (double)moved / dt / 1e9;
+    }
+    if (st) cudaStreamDestroy(st);
+    cudaFree(d);
+    cudaFreeHost(h);
+    return gbps;
 }
 
 // ---- whole-record-loop path: raw FASTA/FASTQ text in, formatted output text out ----

@@ -54,8 +54,10 @@ size_t b3_long_scratch_bytes(size_t total_bytes, size_t n);
 // (scratch: same layout/size as the BLAKE3 long path)
 cudaError_t launch_k12_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
                             uint8_t *out, void *scratch, cudaStream_t st);
+// nt_out != nullptr: the same pass also produces the ntHash digests (8 bytes per record) — `--hash blake3,nthash` reads the
+// residues once
 cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
-                               uint8_t *out, void *scratch, cudaStream_t st);
+                               uint8_t *out, void *scratch, uint8_t *nt_out, cudaStream_t st);
 
 // Normalise pre-pass (seqhasher.go:246-251 materialised): whitespace strip (if strip) + upper-casing
 // (if upper) of the whole CSR batch into out_res / out_offs (n+1) / out_len (n, may be null).

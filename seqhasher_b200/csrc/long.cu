@@ -62,21 +62,33 @@ __device__ __forceinline__ uint4 ldg16_issue(const uint4 *p)
 #endif
 constexpr uint32_t NT16_WORDS = 16 * 256;   // uint64 entries: [rotation 0..15][byte]
 
+// One look-up = PRMT (byte out of the word, ALU pipe) + IMAD (byte * 8 + table base, FMA pipe: the multiplier comes from
+// constant memory so that ptxas cannot turn it into an ALU-pipe LEA) + LDS.64 with the table's offset as an immediate + one
+// LOP3 per half (three-input XORs).  Two ALU instructions per byte: what the fused BLAKE3 + ntHash pass pays on its
+// bounding pipe.
+static __constant__ uint32_t c_eight = 8u;
+template <int I>   // byte I (0..15) of the unit: table 15 - I
+__device__ __forceinline__ void nt_look(uint32_t x, uint32_t base, uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t b = __byte_perm(x, 0, 0x4440 | (I & 3));               // byte I & 3 of the word, zero-extended
+    const uint32_t a = b * c_eight + base;
+    uint32_t l, h;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(l), "=r"(h) : "r"(a), "n"((15 - I) * 2048));
+    lo ^= l;
+    hi ^= h;
+}
 template <bool UPPER>
 __device__ __forceinline__ uint64_t nt_unit16(uint4 v, const uint64_t *lut)
 {
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint64_t t = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t x = UPPER ? upper4(w[k]) : w[k];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t b = __byte_perm(x, 0, 0x4440 | j);             // byte j, zero-extended (one PRMT)
-            t ^= lut[(15 - (4 * k + j)) * 256 + b];
-        }
-    }
-    return t;
+    const uint32_t base = smem_u32(lut);
+    const uint32_t x0 = UPPER ? upper4(v.x) : v.x, x1 = UPPER ? upper4(v.y) : v.y, x2 = UPPER ? upper4(v.z) : v.z,
+                   x3 = UPPER ? upper4(v.w) : v.w;
+    uint32_t lo = 0, hi = 0;
+    nt_look<0>(x0, base, lo, hi); nt_look<1>(x0, base, lo, hi); nt_look<2>(x0, base, lo, hi); nt_look<3>(x0, base, lo, hi);
+    nt_look<4>(x1, base, lo, hi); nt_look<5>(x1, base, lo, hi); nt_look<6>(x1, base, lo, hi); nt_look<7>(x1, base, lo, hi);
+    nt_look<8>(x2, base, lo, hi); nt_look<9>(x2, base, lo, hi); nt_look<10>(x2, base, lo, hi); nt_look<11>(x2, base, lo, hi);
+    nt_look<12>(x3, base, lo, hi); nt_look<13>(x3, base, lo, hi); nt_look<14>(x3, base, lo, hi); nt_look<15>(x3, base, lo, hi);
+    return mk64(lo, hi);
 }
 
 template <bool UPPER>
@@ -157,15 +169,24 @@ cudaError_t launch_nthash_long(bool upper, const uint8_t *res, const int64_t *of
 
 // --------------------------------------------------------------------------------------------- XXH3
 
-// 16 bytes at any address as 4 LE words: two aligned 128-bit loads + funnel shift (m is warp-uniform here)
-template <bool UPPER>
-__device__ __forceinline__ void load16_any(const uint8_t *p, uint32_t (&w)[4])
+// 16 bytes at any address as 4 LE words: two aligned 128-bit loads + funnel shift (m is warp-uniform here).  The loads and
+// the assembly are separate calls so that a caller can issue the loads of its next step before it consumes these.
+struct Raw16 {
+    uint4 a, b;
+};
+__device__ __forceinline__ Raw16 load16_raw(const uint8_t *p)
 {
     const uint4 *q = reinterpret_cast<const uint4 *>((uintptr_t)p & ~(uintptr_t)15);
-    const uint32_t m = (uint32_t)((uintptr_t)p & 15u);
-    const uint4 a = __ldg(q);
-    uint4 b = make_uint4(0, 0, 0, 0);
-    if (m) b = __ldg(q + 1);
+    Raw16 r;
+    r.a = __ldg(q);
+    r.b = make_uint4(0, 0, 0, 0);
+    if ((uintptr_t)p & 15u) r.b = __ldg(q + 1);
+    return r;
+}
+template <bool UPPER>
+__device__ __forceinline__ void assemble16(const Raw16 &r, uint32_t m, uint32_t (&w)[4])
+{
+    const uint4 a = r.a, b = r.b;
     const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     const uint32_t sh = (m & 3u) * 8u;
     switch (m >> 2) {
@@ -190,6 +211,11 @@ __device__ __forceinline__ void load16_any(const uint8_t *p, uint32_t (&w)[4])
 #pragma unroll
         for (int i = 0; i < 4; i++) w[i] = upper4(w[i]);
     }
+}
+template <bool UPPER>
+__device__ __forceinline__ void load16_any(const uint8_t *p, uint32_t (&w)[4])
+{
+    assemble16<UPPER>(load16_raw(p), (uint32_t)((uintptr_t)p & 15u), w);
 }
 
 // 64-bit LE word of the secret copy in shared memory at any byte offset
@@ -231,15 +257,34 @@ __global__ void __launch_bounds__(256) xxh3_warp_kernel(const uint8_t *__restric
         uint64_t a0 = sub == 0 ? init0 : 0, a1 = sub == 0 ? init1 : 0;   // sub 0 carries the state, the others deltas
         const uint64_t nblocks = (len - 1) >> 10;
         const uint32_t tail_stripes = (uint32_t)(((len - 1) - (nblocks << 10)) >> 6);
+        // the loads of block b + 1 are issued before block b is folded and reduced (10 shuffles + the scramble per block would
+        // otherwise leave the memory pipe idle: long-scoreboard stalls were 10 per issue slot)
+        const uint32_t mis = (uint32_t)((uintptr_t)(p + 16u * pair) & 15u);   // the same for every unit of this lane (64 | strides)
+        Raw16 nxt[2];
+#pragma unroll
+        for (uint32_t half = 0; half < 2; half++) {
+            const uint32_t st = sub + 8u * half;
+            nxt[half].a = nxt[half].b = make_uint4(0, 0, 0, 0);
+            if (st < (nblocks ? 16u : tail_stripes)) nxt[half] = load16_raw(p + 64u * st + 16u * pair);
+        }
         for (uint64_t b = 0; b <= nblocks; b++) {
             const bool last = b == nblocks;
             const uint32_t nst = last ? tail_stripes : 16u;
+            Raw16 cur[2] = {nxt[0], nxt[1]};
+            if (!last) {
+                const uint32_t nst_next = (b + 1 == nblocks) ? tail_stripes : 16u;
+#pragma unroll
+                for (uint32_t half = 0; half < 2; half++) {
+                    const uint32_t st = sub + 8u * half;
+                    if (st < nst_next) nxt[half] = load16_raw(p + ((b + 1) << 10) + 64u * st + 16u * pair);
+                }
+            }
 #pragma unroll
             for (uint32_t half = 0; half < 2; half++) {
                 const uint32_t st = sub + 8u * half;
                 if (st < nst) {
                     uint32_t w[4];
-                    load16_any<UPPER>(p + (b << 10) + 64u * st + 16u * pair, w);
+                    assemble16<UPPER>(cur[half], mis, w);
                     const uint64_t d0 = mk64(w[0], w[1]), d1 = mk64(w[2], w[3]);
                     const uint64_t k0 = d0 ^ ssec(sec, 8u * st + 16u * pair), k1 = d1 ^ ssec(sec, 8u * st + 16u * pair + 8u);
                     a0 += d1 + (uint64_t)(uint32_t)k0 * (uint64_t)(uint32_t)(k0 >> 32);
@@ -466,12 +511,28 @@ __device__ __forceinline__ void load_block16(const uint8_t *p, uint32_t (&w)[16]
 // One thread per chunk of the flattened chunk list.  chunk_base[i] = number of chunks before record i
 // (exclusive scan of the counts, chunk_base[n] = total).  Single-chunk records are finished here (ROOT);
 // for the others the chunk CV goes to cvs[global chunk id].
-template <bool UPPER>
+// NT: the same pass also folds the chunk's bytes into its share of the record's ntHash (`--hash blake3,nthash`, config C4:
+// the residues are read once for both).  Byte j of a chunk sits at record position 1024 c + j and carries the rotation
+// (len - 1 - j) mod 64 — the chunk index drops out because 1024 = 0 mod 64 — so a chunk's share is T_c = XOR_j rol(seed[b_j],
+// 63 - j), the same for every 64-byte block of it, and the record's hash is rol(XOR_c T_c, len mod 64).  BLAKE3 is bound by the
+// ALU pipe; the look-ups ride on the LSU / shared-memory path it leaves idle and add one PRMT + one LOP3 per byte to the ALU.
+template <bool UPPER, bool NT>
 __global__ void __launch_bounds__(128) b3_chunks_kernel(const uint8_t *__restrict__ res,
                                                         const int64_t *__restrict__ offs, size_t n,
                                                         const int64_t *__restrict__ chunk_base,
-                                                        uint32_t *__restrict__ cvs, uint8_t *__restrict__ out)
+                                                        uint32_t *__restrict__ cvs, uint8_t *__restrict__ out,
+                                                        uint64_t *__restrict__ nt_part, uint8_t *__restrict__ nt_out)
 {
+    __shared__ uint64_t lut[NT ? NT16_WORDS : 1];
+    if (NT) {
+        for (uint32_t c = threadIdx.x; c < 256; c += blockDim.x) {
+            const uint64_t s = g_nt_seed_table.v[c];
+#pragma unroll
+            for (int r = 0; r < 16; r++) lut[r * 256 + c] = r ? rotl64(s, r) : s;
+        }
+        __syncthreads();
+    }
+    uint64_t nt = 0;
     const int64_t total = chunk_base[n];
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total) return;
@@ -518,19 +579,33 @@ __global__ void __launch_bounds__(128) b3_chunks_kernel(const uint8_t *__restric
             }
             const uint32_t flags = (b == 0 ? (uint32_t)B3_CHUNK_START : 0u) |
                                    (b == nblocks - 1 ? ((uint32_t)B3_CHUNK_END | root) : 0u);
+            if (NT) {
+                // bytes past the chunk's end are zero in m[] (seed 0); group q of the block still owes the rotation 48 - 16 q
+                const uint64_t g0 = nt_unit16<false>(make_uint4(m[0], m[1], m[2], m[3]), lut);
+                const uint64_t g1 = nt_unit16<false>(make_uint4(m[4], m[5], m[6], m[7]), lut);
+                const uint64_t g2 = nt_unit16<false>(make_uint4(m[8], m[9], m[10], m[11]), lut);
+                const uint64_t g3 = nt_unit16<false>(make_uint4(m[12], m[13], m[14], m[15]), lut);
+                nt ^= rotl64_shf(g0, 48) ^ rotl64_shf(g1, 32) ^ rotl64_shf(g2, 16) ^ g3;
+            }
             b3_compress(cv, m, c, 0u, bl, flags);
         }
     }
     uint32_t *dst = root ? reinterpret_cast<uint32_t *>(out + i * 32) : cvs + g * 8;
     *reinterpret_cast<uint4 *>(dst) = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     *reinterpret_cast<uint4 *>(dst + 4) = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+    if (NT) {
+        if (root) store_be64(nt_out + i * 8, rotl64v(nt, (uint32_t)(len & 63)));
+        else nt_part[g] = nt;
+    }
 }
 
 // One thread per record with >= 2 chunks: lazy binary-counter merge of its chunk CVs (same tree as
 // blake3_record in hash_blake3.cuh); empty records get the all-zero slot.
+template <bool NT>
 __global__ void __launch_bounds__(128) b3_merge_kernel(const int64_t *__restrict__ offs, size_t n,
                                                        const int64_t *__restrict__ chunk_base,
-                                                       const uint32_t *__restrict__ cvs, uint8_t *__restrict__ out)
+                                                       const uint32_t *__restrict__ cvs, uint8_t *__restrict__ out,
+                                                       const uint64_t *__restrict__ nt_part, uint8_t *__restrict__ nt_out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -540,9 +615,15 @@ __global__ void __launch_bounds__(128) b3_merge_kernel(const int64_t *__restrict
     if (nchunks == 0) {   // empty-sequence rule
         *reinterpret_cast<uint4 *>(o) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4 *>(o + 4) = make_uint4(0, 0, 0, 0);
+        if (NT) *reinterpret_cast<uint2 *>(nt_out + i * 8) = make_uint2(0u, 0u);
         return;
     }
     if (nchunks == 1) return;   // finished by b3_chunks_kernel
+    if (NT) {
+        uint64_t t = 0;
+        for (uint32_t c = 0; c < nchunks; c++) t ^= __ldg(nt_part + base + c);
+        store_be64(nt_out + i * 8, rotl64v(t, (uint32_t)((offs[i + 1] - offs[i]) & 63)));
+    }
     uint32_t stack[22][8];
     int depth = 0;
     uint32_t cv[8];
@@ -569,12 +650,13 @@ size_t b3_long_scratch_bytes(size_t total_bytes, size_t n)
 {
     const size_t max_chunks = total_bytes / 1024 + n + 1;
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    return up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)) + up(max_chunks * 32) + up(scan_tmp_bytes(n));
+    // counts | chunk bases | 32-byte CVs | scan scratch | 8-byte ntHash shares (blake3 + nthash in one pass)
+    return up(n * sizeof(uint32_t)) + up((n + 1) * sizeof(int64_t)) + up(max_chunks * 32) + up(scan_tmp_bytes(n)) + up(max_chunks * 8);
 }
 
 
 cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *offs, size_t n, size_t total_bytes,
-                               uint8_t *out, void *scratch, cudaStream_t st)
+                               uint8_t *out, void *scratch, uint8_t *nt_out, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -590,9 +672,17 @@ cudaError_t launch_blake3_long(bool upper, const uint8_t *res, const int64_t *of
     if (e != cudaSuccess) return e;
     const size_t max_chunks = total_bytes / 1024 + n + 1;   // upper bound of chunk_base[n]; the kernel re-checks
     const unsigned blocks = (unsigned)((max_chunks + 127) / 128);
-    if (upper) b3_chunks_kernel<true><<<blocks, 128, 0, st>>>(res, offs, n, chunk_base, cvs, out);
-    else b3_chunks_kernel<false><<<blocks, 128, 0, st>>>(res, offs, n, chunk_base, cvs, out);
-    b3_merge_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(offs, n, chunk_base, cvs, out);
+    uint64_t *nt_part = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(scan_tmp) + up(scan_tmp_bytes(n)));
+    const unsigned mblocks = (unsigned)((n + 127) / 128);
+    if (nt_out) {   // blake3 + nthash: one pass over the residues
+        if (upper) b3_chunks_kernel<true, true><<<blocks, 128, 0, st>>>(res, offs, n, chunk_base, cvs, out, nt_part, nt_out);
+        else b3_chunks_kernel<false, true><<<blocks, 128, 0, st>>>(res, offs, n, chunk_base, cvs, out, nt_part, nt_out);
+        b3_merge_kernel<true><<<mblocks, 128, 0, st>>>(offs, n, chunk_base, cvs, out, nt_part, nt_out);
+    } else {
+        if (upper) b3_chunks_kernel<true, false><<<blocks, 128, 0, st>>>(res, offs, n, chunk_base, cvs, out, nullptr, nullptr);
+        else b3_chunks_kernel<false, false><<<blocks, 128, 0, st>>>(res, offs, n, chunk_base, cvs, out, nullptr, nullptr);
+        b3_merge_kernel<false><<<mblocks, 128, 0, st>>>(offs, n, chunk_base, cvs, out, nullptr, nullptr);
+    }
     g_launches += 2;
     return cudaGetLastError();
 }

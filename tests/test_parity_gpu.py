@@ -245,3 +245,26 @@ def test_hash_sharded_single_process(shb, oracle):
     want, wl = oracle.batch(res, offs, ["sha1", "xxh3"], flags=3, threads=4)
     got, gl = hash_sharded(res, offs, ["sha1", "xxh3"], 3, n_gpus)
     assert (gl == wl).all() and (got[0] == want[0]).all() and (got[1] == want[1]).all()
+
+
+def test_blake3_nthash_one_pass_on_long_records(shb, oracle):
+    """`--hash blake3,nthash` on long records (config C4): ntHash is folded into the BLAKE3 chunk pass.  Against the oracle
+    and against the two-pass path (SHB_FLAG_NO_FUSED_B3NT), both case modes; chunk-boundary lengths, empty and
+    single-chunk records mixed in (mean stays above the 10 KiB threshold of the chunk-parallel path)."""
+    import numpy as np
+    rng = np.random.default_rng(77)
+    lens = np.concatenate([[0, 1, 63, 64, 65, 1023, 1024, 1025, 2047, 2048, 2049, 65536, 65537, 40000 * 3 + 1],
+                           rng.integers(10_000, 50_000, size=60)])
+    offs = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    res = rng.choice(np.frombuffer(b"ACGTNacgtnU*-", dtype=np.uint8), size=int(offs[-1]))
+    for flags in (0, shb.FLAG_UPPER):
+        want, _ = oracle.batch(res, offs, ["blake3", "nthash"], flags, threads=4)
+        got, _ = shb.hash_batch(res, offs, ["blake3", "nthash"], flags)
+        two, _ = shb.hash_batch(res, offs, ["blake3", "nthash"], flags | shb.FLAG_NO_FUSED_B3NT)
+        for k in range(2):
+            assert (got[k] == want[k]).all(), (flags, k)
+            assert (two[k] == want[k]).all(), (flags, k)
+        # order of the hash list must not matter, nor other algorithms in between
+        got3, _ = shb.hash_batch(res, offs, ["nthash", "xxh3", "blake3"], flags)
+        assert (got3[0] == want[1]).all() and (got3[2] == want[0]).all()

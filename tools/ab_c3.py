@@ -33,6 +33,7 @@ for name, n, L, algos, flags, lower in %s:
 print(json.dumps(out))
 '''
 CASES = [("c3_150", 20_000_000, 150, ["xxhash", "xxh3", "murmur3"], 1, 20),
+         ("c3_150_uppercase", 20_000_000, 150, ["xxhash", "xxh3", "murmur3"], 1, 0),
          ("c3_150_strip", 20_000_000, 150, ["xxhash", "xxh3", "murmur3"], 3, 20),
          ("c3_100_nocase", 20_000_000, 100, ["xxhash", "xxh3", "murmur3"], 0, 20),
          ("c3_230", 10_000_000, 230, ["xxhash", "xxh3", "murmur3"], 1, 20),

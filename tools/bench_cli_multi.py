@@ -1,0 +1,90 @@
+"""The compiled host (bin/seqhasher-b200) on a large plain FASTA with 1, 2, 4 ... GPUs (SHB_GPUS): whole-process wall time,
+text GB/s, and a byte comparison of the outputs (chunks alternate between the devices, the writer restores chunk order).
+VERDICT r1 #5: "a 4 GB plain FASTA scales past one GPU's 12.9 GB/s".
+
+usage: python tools/bench_cli_multi.py [--gb 4] [--gpus 1,2,4,8] [--hash sha1]"""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "seqhasher_b200", "bin", "seqhasher-b200")
+
+
+def make_fasta(path, gb):
+    """single-line 250-bp records, ~`gb` GB of text, written in 256 MB slabs"""
+    rng = np.random.default_rng(5)
+    L, per_slab = 250, 1_000_000
+    rec_bytes = L + 14
+    n_slabs = max(1, int(gb * 1e9 / (per_slab * rec_bytes)))
+    n = 0
+    with open(path, "wb") as f:
+        for s in range(n_slabs):
+            seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(per_slab, L))
+            rows = np.empty((per_slab, rec_bytes), dtype=np.uint8)
+            ids = np.char.zfill((np.arange(per_slab) + s * per_slab).astype(str), 9)
+            hdr = np.frombuffer(("".join(">r" + i + "\n" for i in ids)).encode(), dtype=np.uint8).reshape(per_slab, 12)
+            rows[:, :12] = hdr
+            rows[:, 12:12 + L] = seq
+            rows[:, 12 + L] = 10
+            rows = rows[:, :13 + L]
+            f.write(rows.tobytes())
+            n += per_slab
+    return n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gb", type=float, default=4.0)
+    ap.add_argument("--gpus", default="1,2,4,8")
+    ap.add_argument("--hash", default="sha1")
+    a = ap.parse_args()
+    import torch
+    have = torch.cuda.device_count()
+    path = "/dev/shm/shb_big.fa" if os.path.isdir("/dev/shm") else "/tmp/shb_big.fa"
+    t0 = time.perf_counter()
+    n = make_fasta(path, a.gb)
+    size = os.path.getsize(path)
+    out = {"file_bytes": size, "records": n, "hash": a.hash, "gen_s": time.perf_counter() - t0, "host_cpus": os.cpu_count(), "runs": []}
+    ref = None
+    for g in [int(x) for x in a.gpus.split(",")]:
+        if g > have:
+            continue
+        env = dict(os.environ, SHB_GPUS=str(g), SHB_TIMING="1")
+        env.pop("CUDA_VISIBLE_DEVICES", None)
+        best, digest, phases = None, None, ""
+        for rep in range(3):
+            t0 = time.perf_counter()
+            p = subprocess.run([CLI, "--headersonly", "--hash", a.hash, path, "/dev/shm/shb_big.out"], capture_output=True, env=env)
+            dt = time.perf_counter() - t0
+            if p.returncode != 0:
+                print("FAILED", g, p.stderr.decode()[-300:])
+                break
+            if best is None or dt < best:
+                best, phases = dt, p.stderr.decode().replace("\n", " | ")
+        h = hashlib.sha256()
+        with open("/dev/shm/shb_big.out", "rb") as f:
+            while True:
+                b = f.read(1 << 24)
+                if not b:
+                    break
+                h.update(b)
+        digest = h.hexdigest()
+        ref = ref or digest
+        r = {"gpus": g, "wall_s": best, "text_gbps": size / best / 1e9, "seqs_per_s": n / best, "output_sha256": digest[:16],
+             "same_output_as_1gpu": digest == ref, "phases": phases}
+        out["runs"].append(r)
+        print(json.dumps(r), flush=True)
+    os.remove(path)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "cli_multi.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
