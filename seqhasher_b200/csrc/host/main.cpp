@@ -17,6 +17,7 @@
 #include <vector>
 
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../../include/seqhash_b200.h"
 #include "decompress.hpp"
@@ -457,9 +458,333 @@ int process_sequences(host::Source &in, FILE *out, const Config &cfg, int n_gpus
     return rc;
 }
 
-// How many GPUs this run uses: SHB_GPUS if set; otherwise one per 2 GiB of a plain regular file (creating a CUDA
-// context costs 0.1-0.25 s per device, one GPU runs the record loop at about 13 GB/s of text), one for anything else
-// (a compressed input is bound by its host-side inflate, not by the GPU).
+// ---- plain regular files: every chunk slot reads its own byte range ----
+//
+// A sequential reader tops out at one thread's page-cache copy rate (~10 GB/s with four pread helpers), below what a single
+// B200 takes (~13 GB/s of text), so more GPUs cannot help a stream.  A seekable plain file needs no reader at all: chunk k
+// is the records that START in [first + k C, first + (k + 1) C); its slot preads that range (plus the tail of the record that
+// crosses the upper bound) straight into its pinned buffer and finds both boundaries itself with the splitter's own rule — a
+// FASTA record starts at a line-initial '>', a FASTQ record at a line that starts with '@' and whose next-but-one line starts
+// with '+'.  Neighbouring slots compute the shared boundary from the same bytes with the same rule, so no record is lost or
+// taken twice; the writer emits the chunks in order (seqhasher.go:227-283 is one sequential loop).
+
+constexpr size_t kNpos = (size_t)-1;
+constexpr size_t kNeedMore = (size_t)-2;
+
+// first record start at buffer index >= from (from > 0: buf[from - 1] is readable); kNpos: none in buf[0, n); kNeedMore:
+// a FASTQ candidate whose next-but-one line lies beyond the buffer (only when !at_eof)
+size_t find_record_start(const uint8_t *buf, size_t n, size_t from, int format, bool at_eof)
+{
+    if (format == SHB_FORMAT_FASTA) {
+        size_t p = from;
+        while (p < n) {
+            const void *q = memchr(buf + p, '>', n - p);
+            if (!q) return kNpos;
+            p = (size_t)((const uint8_t *)q - buf);
+            if (p == 0 || buf[p - 1] == '\n') return p;
+            p++;
+        }
+        return kNpos;
+    }
+    // FASTQ: walk the line starts from `from` on
+    size_t ls = from;
+    if (from > 0 && buf[from - 1] != '\n') {
+        const void *q = memchr(buf + from, '\n', n - from);
+        if (!q) return at_eof ? kNpos : kNeedMore;
+        ls = (size_t)((const uint8_t *)q - buf) + 1;
+    }
+    while (ls < n) {
+        const void *q1 = memchr(buf + ls, '\n', n - ls);
+        if (!q1) return at_eof ? kNpos : kNeedMore;
+        const size_t l1 = (size_t)((const uint8_t *)q1 - buf) + 1;
+        if (buf[ls] == '@') {
+            const void *q2 = l1 < n ? memchr(buf + l1, '\n', n - l1) : nullptr;
+            if (!q2) { if (at_eof) return kNpos; return kNeedMore; }
+            const size_t l2 = (size_t)((const uint8_t *)q2 - buf) + 1;
+            if (l2 >= n) { if (at_eof) return kNpos; return kNeedMore; }
+            if (buf[l2] == '+') return ls;
+        }
+        ls = l1;
+    }
+    return kNpos;
+}
+
+struct RangeJob {
+    int fd = -1;
+    size_t file_size = 0, first = 0, C = 0;
+};
+
+struct RangeSlot {
+    int device = 0;
+    shb_textproc *tp = nullptr;
+    size_t cap = 0;
+    uint8_t *buf = nullptr;
+    int rc = 0;
+    std::string err;
+    std::vector<uint8_t> acc;
+    size_t n_empty = 0, n_nonascii = 0;
+    long long ready = -1, done = -1, freed = -1;
+    bool quit = false;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::thread worker;
+};
+
+size_t pread_full(int fd, uint8_t *dst, size_t n, size_t off)
+{
+    size_t got = 0;
+    while (got < n) {
+        const ssize_t r = pread(fd, dst + got, n - got, (off_t)(off + got));
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    return got;
+}
+
+void range_worker(RangeSlot *s, const RunArgs *a, const RangeJob *job, size_t cap0)
+{
+    // the slot's textproc is created here, on its own thread: the CUDA contexts of several devices come up side by side
+    s->tp = shb_textproc_create(s->device, cap0);
+    if (s->tp) { s->cap = cap0; s->buf = shb_textproc_input(s->tp); }
+    else s->err = std::string("seqhash_b200: ") + shb_last_error();
+    long long seq = -1;
+    while (true) {
+        {
+            std::unique_lock<std::mutex> lk(s->mu);
+            s->cv.wait(lk, [&] { return s->quit || s->ready > seq; });
+            if (s->ready <= seq) return;
+            seq = s->ready;
+        }
+        s->acc.clear();
+        s->n_empty = s->n_nonascii = 0;
+        int rc = 0;
+        if (!s->tp) {
+            rc = -1;
+        } else {
+            s->err.clear();
+            const size_t lo_nom = job->first + (size_t)seq * job->C;
+            const size_t hi_nom = std::min(job->file_size, lo_nom + job->C);
+            const size_t read_lo = seq == 0 ? lo_nom : lo_nom - 1;
+            size_t n = pread_full(job->fd, s->buf, std::min(s->cap, job->file_size - read_lo), read_lo);
+            bool at_eof = read_lo + n >= job->file_size;
+            auto grow = [&]() -> bool {   // more room (a record longer than the slack): a bigger textproc, then read on
+                if (s->cap >= ((size_t)1 << 31)) return false;
+                const size_t ncap = std::min((size_t)1 << 31, s->cap * 4);
+                shb_textproc *t = shb_textproc_create(s->device, ncap);
+                if (!t) return false;
+                memcpy(shb_textproc_input(t), s->buf, n);
+                shb_textproc_destroy(s->tp);
+                s->tp = t; s->cap = ncap; s->buf = shb_textproc_input(t);
+                n += pread_full(job->fd, s->buf + n, std::min(s->cap - n, job->file_size - (read_lo + n)), read_lo + n);
+                at_eof = read_lo + n >= job->file_size;
+                return true;
+            };
+            size_t start = 0, end = 0;
+            bool ok = true;
+            if (seq > 0) {
+                while (true) {
+                    start = find_record_start(s->buf, n, 1, a->format, at_eof);
+                    if (start != kNeedMore) break;
+                    if (!grow()) { ok = false; break; }
+                }
+                if (ok && (start == kNpos || read_lo + start >= hi_nom)) start = kNpos;   // no record starts in this range
+            }
+            if (ok && start != kNpos) {
+                if (hi_nom >= job->file_size) {
+                    while (!at_eof) { if (!grow()) { ok = false; break; } }
+                    end = n;
+                    while (end > start && is_blank(s->buf[end - 1])) end--;   // trailing blank lines are not records
+                } else {
+                    while (true) {
+                        end = find_record_start(s->buf, n, hi_nom - read_lo, a->format, at_eof);
+                        if (end != kNeedMore && !(end == kNpos && !at_eof)) break;
+                        if (!grow()) { ok = false; break; }
+                    }
+                    if (ok && end == kNpos) {   // the file ends inside this chunk's last record
+                        end = n;
+                        while (end > start && is_blank(s->buf[end - 1])) end--;
+                    }
+                }
+            }
+            if (!ok) {
+                rc = -1;
+                s->err = "record larger than the GPU text buffer";
+            } else if (start != kNpos && end > start) {
+                if (start) memmove(s->buf, s->buf + start, end - start);
+                size_t len = end - start;
+                while (true) {
+                    rc = shb_textproc_run(s->tp, len, a->format, 1, a->ids.empty() ? nullptr : a->ids.data(), (int)a->ids.size(),
+                                          a->flags, a->headers_only, a->label);
+                    if (rc < 0) { s->err = shb_last_error(); break; }
+                    s->n_empty += shb_textproc_empty_records(s->tp);
+                    s->n_nonascii += shb_textproc_nonascii(s->tp);
+                    const size_t used = shb_textproc_consumed(s->tp);
+                    if (rc != 0 || used == 0 || used >= len) break;   // else: record index full, run the rest
+                    size_t nout = 0;
+                    const uint8_t *o = shb_textproc_output(s->tp, &nout);
+                    s->acc.insert(s->acc.end(), o, o + nout);
+                    memmove(s->buf, s->buf + used, len - used);
+                    len -= used;
+                }
+            } else {
+                shb_textproc_run(s->tp, 0, a->format, 1, nullptr, 0, a->flags, a->headers_only, a->label);   // clears the last output
+            }
+        }
+        s->rc = rc;
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            s->done = seq;
+        }
+        s->cv.notify_all();
+    }
+}
+
+int process_file_ranges(int fd, size_t file_size, FILE *out, const Config &cfg, int n_gpus, std::string &err)
+{
+    std::string label = cfg.input;
+    bool no_file_name = cfg.no_file_name;
+    if (!cfg.name_override.empty()) label = cfg.name_override;
+    RunArgs args;
+    for (const std::string &t : cfg.hash_types) {
+        int id = shb_algo_id(t.c_str());
+        args.ids.push_back(id < 0 ? SHB_SHA1 : id);
+    }
+    if (args.ids.size() > 48) { err = "at most 48 hash fields per record are supported by the GPU formatter"; return 1; }
+    args.flags = cfg.case_sensitive ? 0u : SHB_FLAG_UPPER;
+    args.headers_only = cfg.headers_only ? 1 : 0;
+    args.label = no_file_name ? nullptr : label.c_str();
+    RangeJob job;
+    job.fd = fd;
+    job.file_size = file_size;
+    job.C = (size_t)64 << 20;
+    if (const char *e = getenv("SHB_CHUNK_KB")) {
+        const long kb = atol(e);
+        if (kb >= 1) job.C = (size_t)kb << 10;
+    }
+    // sniff: the first non-blank byte decides (fastx.NewReaderFromIO, seqhasher.go:221)
+    {
+        uint8_t head[4096];
+        size_t pos = 0;
+        bool found = false;
+        while (pos < file_size && !found) {
+            const size_t got = pread_full(fd, head, std::min(sizeof head, file_size - pos), pos);
+            if (got == 0) break;
+            for (size_t i = 0; i < got; i++)
+                if (!is_blank(head[i])) { job.first = pos + i; found = true; break; }
+            pos += got;
+        }
+        if (!found) return 0;   // empty input: no records
+        uint8_t c = 0;
+        pread_full(fd, &c, 1, job.first);
+        if (c == '>') args.format = SHB_FORMAT_FASTA;
+        else if (c == '@') args.format = SHB_FORMAT_FASTQ;
+        else { err = "Failed to create reader: fastx: invalid FASTA/Q format"; return 1; }
+    }
+    const long long nchunks = (long long)((file_size - job.first + job.C - 1) / job.C);
+    // four slots per GPU: a slot's pread is one thread copying out of the page cache (5-6 GB/s), a B200 takes ~13 GB/s of text
+    int per_gpu = 4;
+    if (const char *e = getenv("SHB_SLOTS_PER_GPU")) { const int v = atoi(e); if (v >= 1 && v <= 16) per_gpu = v; }
+    const int K = (int)std::min<long long>((long long)per_gpu * n_gpus, nchunks);
+    phase("before create");
+    std::vector<std::unique_ptr<RangeSlot>> slots;
+    const size_t cap0 = job.C + job.C / 4 + 4096;
+    for (int k = 0; k < K; k++) {
+        slots.emplace_back(new RangeSlot());
+        slots[k]->device = k % n_gpus;
+        slots[k]->worker = std::thread(range_worker, slots[k].get(), &args, &job, cap0);
+    }
+    std::mutex wmu;
+    std::condition_variable wcv;
+    long long submitted = -1;
+    bool dispatch_done = false;
+    int rc = 0;
+    const bool allow_nonascii = getenv("SHB_ALLOW_NONASCII") != nullptr;
+    std::atomic<bool> failed{false};
+    std::thread writer([&] {
+        for (long long seq = 0;; seq++) {
+            {
+                std::unique_lock<std::mutex> lk(wmu);
+                wcv.wait(lk, [&] { return submitted >= seq || dispatch_done; });
+                if (submitted < seq) return;
+            }
+            RangeSlot &s = *slots[seq % K];
+            {
+                std::unique_lock<std::mutex> lk(s.mu);
+                s.cv.wait(lk, [&] { return s.done >= seq; });
+            }
+            if (seq == 0) phase("first chunk done");
+            if (rc == 0) {
+                if (s.rc < 0) {
+                    err = (s.tp ? "Error reading record: " : "") + s.err;
+                    rc = 1;
+                } else if (s.n_nonascii && !allow_nonascii) {
+                    err = "Error reading record: non-ASCII bytes in sequence data are not supported "
+                          "(set SHB_ALLOW_NONASCII=1 to hash them as plain bytes)";
+                    rc = 1;
+                } else {
+                    size_t nout = 0;
+                    const uint8_t *o = shb_textproc_output(s.tp, &nout);
+                    if ((!s.acc.empty() && fwrite(s.acc.data(), 1, s.acc.size(), out) != s.acc.size()) ||
+                        (nout && fwrite(o, 1, nout, out) != nout)) {
+                        err = std::string("Error writing record: ") + strerror(errno);
+                        rc = 1;
+                    }
+                    for (size_t k = 0; k < s.n_empty * args.ids.size(); k++) fprintf(stderr, "%s\n", kEmptyMsg);
+                    if (rc == 0 && s.rc == SHB_PARTIAL_FORMAT) {
+                        err = "Error reading record: fastx: invalid FASTA/Q format";
+                        rc = 1;
+                    }
+                }
+                if (rc) failed = true;
+            }
+            {
+                std::lock_guard<std::mutex> lk(s.mu);
+                s.freed = seq;
+            }
+            s.cv.notify_all();
+        }
+    });
+    for (long long seq = 0; seq < nchunks && !failed; seq++) {
+        RangeSlot &s = *slots[seq % K];
+        if (seq >= K) {
+            std::unique_lock<std::mutex> lk(s.mu);
+            s.cv.wait(lk, [&] { return s.freed >= seq - K; });
+        }
+        {
+            std::lock_guard<std::mutex> lk(s.mu);
+            s.ready = seq;
+        }
+        s.cv.notify_all();
+        {
+            std::lock_guard<std::mutex> lk(wmu);
+            submitted = seq;
+        }
+        wcv.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(wmu);
+        dispatch_done = true;
+    }
+    wcv.notify_all();
+    writer.join();
+    for (auto &sp : slots) {
+        {
+            std::lock_guard<std::mutex> lk(sp->mu);
+            sp->quit = true;
+        }
+        sp->cv.notify_all();
+        if (sp->worker.joinable()) sp->worker.join();
+    }
+    if (fflush(out) != 0 || ferror(out)) {
+        if (rc == 0) { err = std::string("Error writing record: ") + strerror(errno); rc = 1; }
+    }
+    phase("records done");
+    return rc;
+}
+
+// How many GPUs this run uses: SHB_GPUS if set; otherwise one per 12 GiB of a plain regular file — bringing up one more
+// device costs 0.3-0.6 s of CUDA initialisation on a cold driver, the time one GPU needs for 4-8 GB of text — and one for
+// anything else (a stream is bound by its reader or its host-side inflate, not by the GPU).
 int pick_gpus(FILE *fin, bool regular_plain)
 {
     if (const char *e = getenv("SHB_GPUS")) {
@@ -469,7 +794,7 @@ int pick_gpus(FILE *fin, bool regular_plain)
     if (!regular_plain) return 1;
     struct stat st;
     if (fstat(fileno(fin), &st) != 0 || !S_ISREG(st.st_mode)) return 1;
-    const long long per = 2LL << 30;
+    const long long per = 12LL << 30;
     long long n = (st.st_size + per - 1) / per;
     return (int)(n < 1 ? 1 : n > 8 ? 8 : n);
 }
@@ -541,7 +866,15 @@ int main(int argc, char **argv)
             err = std::string("seqhash_b200: ") + shb_last_error();
         } else {
             if (n_gpus > have) n_gpus = have;
-            rc = process_sequences(*src, fout, cfg, n_gpus, err);
+            struct stat st;
+            const bool plain_file = fin != stdin && !compressed && fstat(fileno(fin), &st) == 0 && S_ISREG(st.st_mode);
+            size_t chunk = (size_t)64 << 20;
+            if (const char *e = getenv("SHB_CHUNK_KB")) { const long kb = atol(e); if (kb >= 1) chunk = (size_t)kb << 10; }
+            // a seekable plain file of several chunks: every slot reads its own byte range (no sequential reader)
+            if (plain_file && !getenv("SHB_NO_RANGES") && (n_gpus > 1 || (size_t)st.st_size >= 4 * chunk))
+                rc = process_file_ranges(fileno(fin), (size_t)st.st_size, fout, cfg, n_gpus, err);
+            else
+                rc = process_sequences(*src, fout, cfg, n_gpus, err);
         }
     } catch (const std::exception &e) {
         err = std::string("Error reading record: ") + e.what();
