@@ -191,6 +191,9 @@ double shb_probe_int_peak(int device, int kind, int iters);
  * if asked), first touched by the calling thread, copied with plain cudaMemcpyAsync in `piece`-byte pieces for `seconds`.  The
  * roof of the end-to-end numbers; tools/h2d_roof.py runs it from one process per GPU at once. */
 double shb_probe_h2d(int device, size_t bytes, size_t piece, double seconds, int write_combined);
+/* Debug builds of the library (-DSHB_BOUNDS): shared-memory accesses of the tile path that fell outside the CTA's window since
+ * the library was loaded; -1 in a normal build (no checks compiled in).  tools/bounds_check.py. */
+long long shb_debug_oob(void);
 /* XOR checksum of the final states of the last SHA-1 probe (every variant must give the same value). */
 unsigned shb_probe_last_checksum(void);
 

@@ -32,7 +32,7 @@ EXPORTS = [
     "shb_digest_size", "shb_batch_create", "shb_batch_create_on", "shb_batch_destroy", "shb_batch_residues",
     "shb_batch_offsets", "shb_submit", "shb_wait", "shb_digests", "shb_out_lengths", "shb_out_offsets",
     "shb_out_residues", "shb_batch_nonascii", "shb_textproc_nonascii", "shb_scratch_bytes", "shb_hash_device", "shb_launch_count", "shb_synth_fill",
-    "shb_probe_int_peak", "shb_probe_last_checksum", "shb_probe_h2d", "shb_textproc_create", "shb_textproc_destroy",
+    "shb_probe_int_peak", "shb_probe_last_checksum", "shb_probe_h2d", "shb_debug_oob", "shb_textproc_create", "shb_textproc_destroy",
     "shb_textproc_input", "shb_textproc_capacity", "shb_textproc_run", "shb_textproc_output", "shb_textproc_consumed",
     "shb_textproc_records", "shb_textproc_empty_records", "shb_textproc_last_ms",
 ]
@@ -88,6 +88,7 @@ def lib() -> ctypes.CDLL:
     L.shb_probe_int_peak.argtypes = [c.c_int, c.c_int, c.c_int]; L.shb_probe_int_peak.restype = c.c_double
     L.shb_probe_last_checksum.argtypes = []; L.shb_probe_last_checksum.restype = c.c_uint
     L.shb_probe_h2d.argtypes = [c.c_int, c.c_size_t, c.c_size_t, c.c_double, c.c_int]; L.shb_probe_h2d.restype = c.c_double
+    L.shb_debug_oob.argtypes = []; L.shb_debug_oob.restype = c.c_longlong
     L.shb_textproc_create.argtypes = [c.c_int, c.c_size_t]; L.shb_textproc_create.restype = c.c_void_p
     L.shb_textproc_destroy.argtypes = [c.c_void_p]; L.shb_textproc_destroy.restype = None
     L.shb_textproc_input.argtypes = [c.c_void_p]; L.shb_textproc_input.restype = c.c_void_p

@@ -293,6 +293,7 @@ const char *shb_algo_name(int algo) { return (algo >= 0 && algo < SHB_N_ALGOS) ?
 size_t shb_digest_size(int algo) { return (algo >= 0 && algo < SHB_N_ALGOS) ? (size_t)shb::digest_size(algo) : 0; }
 
 unsigned long long shb_launch_count(void) { return shb::g_launches.load(); }
+long long shb_debug_oob(void) { return shb::tile_debug_bounds_build() ? (long long)shb::tile_debug_oob() : -1; }
 
 size_t shb_scratch_bytes(size_t total_bytes, size_t n_records) { return ScratchLayout(total_bytes, n_records).total; }
 

@@ -117,6 +117,7 @@ struct GroupReader {
     {
         w = reinterpret_cast<const uint32_t *>(tile + (start & ~3u));
         sh = (start & 3u) * 8u;
+        smem_check(w, 4);
         prev = *w++;
         wsf = 0;
     }
@@ -124,6 +125,7 @@ struct GroupReader {
     // (only the whitespace test looks at it: bytes past the record end must not raise the flag)
     __device__ __forceinline__ void next_raw(uint32_t (&d)[4], uint32_t valid = 16)
     {
+        smem_check(w, 16);
         const uint32_t n0 = w[0], n1 = w[1], n2 = w[2], n3 = w[3];
         w += 4;
         d[0] = __funnelshift_r(prev, n0, sh);
@@ -183,6 +185,7 @@ __device__ __forceinline__ void read16_any(const uint8_t *tile, uint32_t pos, ui
 {
     const uint32_t *q = reinterpret_cast<const uint32_t *>(tile + (pos & ~3u));
     const uint32_t s = (pos & 3u) * 8u;
+    smem_check(q, 20);
     const uint32_t a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
     uint32_t x0 = __funnelshift_r(a, b, s), x1 = __funnelshift_r(b, c, s), x2 = __funnelshift_r(c, d, s), x3 = __funnelshift_r(d, e, s);
     if (UPPER && (!F3_UPPER_SKIP || ((x0 | x1 | x2 | x3) & 0x20202020u) != 0)) { x0 = f3_upper(x0); x1 = f3_upper(x1); x2 = f3_upper(x2); x3 = f3_upper(x3); }

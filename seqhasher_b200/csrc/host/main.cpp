@@ -681,8 +681,10 @@ int process_file_ranges(int fd, size_t file_size, FILE *out, const Config &cfg, 
         else { err = "Failed to create reader: fastx: invalid FASTA/Q format"; return 1; }
     }
     const long long nchunks = (long long)((file_size - job.first + job.C - 1) / job.C);
-    // four slots per GPU: a slot's pread is one thread copying out of the page cache (5-6 GB/s), a B200 takes ~13 GB/s of text
-    int per_gpu = 4;
+    // Slots: a slot's pread is one thread copying out of the page cache (5-6 GB/s) and a B200 takes ~13 GB/s of text, so one
+    // GPU gets four; with more GPUs two each are enough readers, and every slot costs ~0.1 s to set up (80 MB of pinned
+    // memory, ~0.5 GB of device buffers) — 32 slots on an 8-GPU box delayed the first chunk by 2.6 s.
+    int per_gpu = n_gpus == 1 ? 4 : 2;
     if (const char *e = getenv("SHB_SLOTS_PER_GPU")) { const int v = atoi(e); if (v >= 1 && v <= 16) per_gpu = v; }
     const int K = (int)std::min<long long>((long long)per_gpu * n_gpus, nchunks);
     phase("before create");

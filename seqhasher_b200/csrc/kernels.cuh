@@ -43,6 +43,8 @@ cudaError_t launch_hash_tile(uint32_t mask, bool upper, const uint8_t *res, cons
                              uint8_t *const *outs, uint32_t cap, uint8_t *strip_scratch, int64_t *out_len,
                              cudaStream_t st);
 uint32_t tile_fast_mask();
+unsigned long long tile_debug_oob();   // -DSHB_BOUNDS builds: out-of-window shared-memory accesses of the tile path so far
+bool tile_debug_bounds_build();
 
 // Long-record path (long.cu): ntHash warp-per-record; BLAKE3 thread-per-chunk over the flattened chunk
 // list + thread-per-record tree merge (scratch: b3_long_scratch_bytes()).

@@ -64,6 +64,7 @@ __device__ __noinline__ uint32_t strip_in_smem(uint8_t *tile, uint32_t start, ui
 {
     uint32_t j = start;
     for (uint32_t i = start; i < start + len; i++) {
+        smem_check(tile + i, 1);
         const uint8_t c = tile[i];
         if (!is_ws(c)) tile[j++] = c;
     }
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
                 uint4 *t4 = reinterpret_cast<uint4 *>(tile);
                 uint32_t f = 0;
                 for (uint32_t k = threadIdx.x; k < (bytes >> 4); k += blockDim.x) {
+                    smem_check(t4 + k, 16);
                     uint4 v = t4[k];
                     if (STRIP) f |= has_byte_below_0x21(v.x) | has_byte_below_0x21(v.y) | has_byte_below_0x21(v.z) |
                                     has_byte_below_0x21(v.w);
@@ -202,7 +204,10 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
             // whitespace to the speculative strip and send that record through the compaction + second hash while
             // its CTA waits (a 1.5x slowdown once the garbage happened to be small values).  Its owner, the only
             // thread that reads them, makes them letters first.
-            if (SPECULATE && i + 1 == r1) *reinterpret_cast<uint2 *>(tile + bytes) = make_uint2(0x41414141u, 0x41414141u);
+            if (SPECULATE && i + 1 == r1) {
+                smem_check(tile + bytes, 8);
+                *reinterpret_cast<uint2 *>(tile + bytes) = make_uint2(0x41414141u, 0x41414141u);
+            }
             for (int pass = 0;; pass++) {
                 bool cand;
                 if (FUSED3 && len >= 17u && len <= 240u) {
@@ -293,5 +298,26 @@ cudaError_t launch_hash_tile(uint32_t mask, bool upper, const uint8_t *res, cons
 }
 
 uint32_t tile_fast_mask() { return FAST_MASK; }
+
+// shared-memory accesses of the tile path outside the CTA's window, counted by a -DSHB_BOUNDS build (0 otherwise)
+unsigned long long tile_debug_oob()
+{
+#ifdef SHB_BOUNDS
+    unsigned long long v = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&v, g_smem_oob, sizeof v);
+    return v;
+#else
+    return 0;
+#endif
+}
+bool tile_debug_bounds_build()
+{
+#ifdef SHB_BOUNDS
+    return true;
+#else
+    return false;
+#endif
+}
 
 }  // namespace shb

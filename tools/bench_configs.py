@@ -70,7 +70,7 @@ def main():
     out = []
     if "C3" in only:
         out.append(run("C3: 150-bp Illumina reads, xxhash,xxh3,murmur3 fused, upper", int(100_000_000 * a.scale), 150,
-                       ["xxhash", "xxh3", "murmur3"], B.FLAG_UPPER, 0xC3, 20, 1, a.steps, hbm))
+                       ["xxhash", "xxh3", "murmur3"], B.FLAG_UPPER, 0xC3, 0, 0, a.steps, hbm))
     if "C4" in only:
         out.append(run("C4: 10-50 kb nanopore-like reads, blake3+nthash, case-sensitive", int(1_000_000 * a.scale),
                        (10_000, 50_000), ["blake3", "nthash"], 0, 0xC4, 0, 1, a.steps, hbm))
