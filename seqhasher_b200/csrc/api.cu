@@ -166,6 +166,10 @@ int run_pipeline(const uint8_t *d_res, const int64_t *d_offs, size_t n, size_t t
         for (int a = 0; a < SHB_N_ALGOS; a++) {
             if (!(want >> a & 1u)) continue;
             if (b3_nt_fused && a == SHB_NTHASH) continue;
+            if (a == SHB_RAPIDHASH32 && (want >> SHB_RAPIDHASH & 1u)) {   // a fold of rapidhash, which ran just before (a = 10)
+                CU(shb::launch_rapid_fold32(slot_of[SHB_RAPIDHASH], n, slot_of[a], st));
+                continue;
+            }
             if (long_ok && a == SHB_NTHASH && mean >= nt_warp_min) {
                 CU(shb::launch_nthash_long(fused_upper, res, offs, n, slot_of[a], st));
             } else if (long_ok && a == SHB_XXH3 && mean >= xxh3_warp_min) {

@@ -328,20 +328,21 @@ __device__ __forceinline__ uint4 load16_guarded(const uint8_t *res, size_t pos, 
 
 template <bool STRIP>
 __global__ void __launch_bounds__(256) nz_count_kernel(const uint8_t *__restrict__ res, size_t total,
-                                                       uint32_t *__restrict__ block_counts)
+                                                       uint32_t *__restrict__ block_counts, size_t nb)
 {
-    const size_t pos = (size_t)blockIdx.x * NORM_BLK + 16u * threadIdx.x;
-    uint32_t cnt = __popc(keep_mask16<STRIP>(load16_guarded(res, pos, total), pos, total));
-    __shared__ uint32_t s_w[8];
-    for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
+    // one warp per 4 KiB block, eight 128-bit loads in flight per lane (one unit per thread and one block per CTA left the
+    // memory pipe at 1.7 TB/s)
+    const size_t blk = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (blk >= nb) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t cnt = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) t += s_w[i];
-        block_counts[blockIdx.x] = t;
+    for (int k = 0; k < 8; k++) {
+        const size_t pos = blk * NORM_BLK + 16u * (lane + 32u * k);
+        cnt += __popc(keep_mask16<STRIP>(load16_guarded(res, pos, total), pos, total));
     }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) block_counts[blk] = cnt;
 }
 
 // exclusive scan of nb block counts into nb+1 prefixes; one CTA of 1024 threads
@@ -488,19 +489,90 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint8_t *__restrict_
     s_excl[threadIdx.x] = excl;
     s_mask[threadIdx.x] = mask;
     const int64_t bp = block_prefix[blockIdx.x];
-    // kept bytes of this thread go to out_res[bp + excl ...]
-    {
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        if (UPPER) {
+    // The block's kept bytes form one contiguous run out_res[bp, bp + blk_total).  They are compacted in shared memory at the
+    // same 16-byte phase as their destination and copied out with aligned 128-bit stores (byte stores straight to global
+    // memory made this kernel 0.85 TB/s: 17.9 of the 83.7 ms of config C5, profiles/r02_launches_bench.csv).
+    __shared__ __align__(16) uint8_t s_out[NORM_BLK + 32];
+    __shared__ uint4 s_last[8];                                    // every warp's last unit, for the next warp's first lane
+    const uint32_t phase = (uint32_t)(bp & 15);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (UPPER) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) w[k] = upper4(w[k]);
+        for (int k = 0; k < 4; k++) w[k] = upper4(w[k]);
+    }
+    uint32_t blk_total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) blk_total += s_w[i];
+    const uint32_t blk_valid = (uint32_t)(total - bstart < NORM_BLK ? total - bstart : NORM_BLK);
+    uint8_t *gbase = out_res + (bp - phase);                       // 16-byte aligned: out_res is, and bp - phase is a multiple of 16
+    const uint32_t end = phase + blk_total;                        // the block's bytes are [phase, end) of the window at gbase
+    if (blk_total == blk_valid) {
+        // Nothing to drop in this block (the usual case: a reader has removed the line breaks already): the output is the input
+        // moved by a constant, so every thread builds one ALIGNED 16-byte output unit from its own unit and its left
+        // neighbour's (shuffle; the warp's first lane takes it from the previous warp through shared memory) and stores it
+        // straight to global memory.  Staging through shared memory costs 16 byte stores per thread at a 16-byte lane stride,
+        // a 4-way bank conflict each: 14 of the 78 ms of config C5.
+        if ((threadIdx.x & 31) == 31) s_last[threadIdx.x >> 5] = make_uint4(w[0], w[1], w[2], w[3]);
+        __syncthreads();
+        uint32_t pw[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pw[k] = __shfl_up_sync(0xffffffffu, w[k], 1);
+        if ((threadIdx.x & 31) == 0 && threadIdx.x) {
+            const uint4 q = s_last[(threadIdx.x >> 5) - 1];
+            pw[0] = q.x; pw[1] = q.y; pw[2] = q.z; pw[3] = q.w;
         }
-        uint8_t *dst = out_res + bp + excl;
+        // window = [left neighbour's 16 bytes | my 16 bytes]; my output unit starts `phase` bytes before my own bytes
+        const uint32_t W[8] = {pw[0], pw[1], pw[2], pw[3], w[0], w[1], w[2], w[3]};
+        const uint32_t ws = phase >> 2, sh = 32u - 8u * (phase & 3u);   // sh = 32: whole words, funnelshift_rc clamps to "take the high word"
+        uint32_t o[4];
+        switch (ws) {                                                // uniform over the block
+        case 0:
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = __funnelshift_rc(W[3 + j], W[4 + j], sh);
+            break;
+        case 1:
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = __funnelshift_rc(W[2 + j], W[3 + j], sh);
+            break;
+        case 2:
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = __funnelshift_rc(W[1 + j], W[2 + j], sh);
+            break;
+        default:
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = __funnelshift_rc(W[0 + j], W[1 + j], sh);
+            break;
+        }
+        const uint32_t lo16 = 16u * threadIdx.x, hi16 = lo16 + 16u;
+        if (lo16 >= phase && hi16 <= end) {
+            *reinterpret_cast<uint4 *>(gbase + lo16) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else if (lo16 < end) {                                     // the first unit (shared with the previous block) or the last valid one
+            for (uint32_t k = (lo16 > phase ? lo16 : phase); k < (hi16 < end ? hi16 : end); k++)
+                gbase[k] = (uint8_t)(o[(k - lo16) >> 2] >> (8 * ((k - lo16) & 3)));
+        }
+        // the spill-over unit: the last `phase` bytes of the block land in the unit after the last thread's
+        if (phase && threadIdx.x == blockDim.x - 1 && hi16 < end) {
+            for (uint32_t k = hi16; k < end; k++) {
+                const uint32_t srcb = k - phase - lo16;             // byte of my own unit
+                gbase[k] = (uint8_t)(w[srcb >> 2] >> (8 * (srcb & 3)));
+            }
+        }
+    } else {
+        uint8_t *dst = s_out + phase + excl;
         uint32_t m = mask;
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             if (m & 1u) *dst++ = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
             m >>= 1;
+        }
+        __syncthreads();
+        for (uint32_t u = threadIdx.x; u * 16u < end; u += blockDim.x) {
+            const uint32_t lo16 = u * 16u, hi16 = lo16 + 16u;
+            if (lo16 >= phase && hi16 <= end) {
+                *reinterpret_cast<uint4 *>(gbase + lo16) = *reinterpret_cast<const uint4 *>(s_out + lo16);
+            } else {                                                 // the run's first / last unit is shared with the neighbouring block
+                for (uint32_t k = (lo16 > phase ? lo16 : phase); k < (hi16 < end ? hi16 : end); k++) gbase[k] = s_out[k];
+            }
         }
     }
     __syncthreads();
@@ -525,6 +597,24 @@ __global__ void lengths_kernel(const int64_t *__restrict__ offs, size_t n, int64
     if (i < n) out_len[i] = offs[i + 1] - offs[i];
 }
 
+// rapidhash32 from finished rapidhash digests (both big-endian in memory): lo32 ^ hi32, seqhasher.go:340-343
+__global__ void rapid_fold32_kernel(const uint2 *__restrict__ h64, size_t n, uint32_t *__restrict__ h32)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint2 v = h64[i];
+        h32[i] = v.x ^ v.y;   // an XOR of the halves commutes with the byte order
+    }
+}
+
+cudaError_t launch_rapid_fold32(const uint8_t *h64, size_t n, uint8_t *h32, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    rapid_fold32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint2 *>(h64), n, reinterpret_cast<uint32_t *>(h32));
+    g_launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lengths(const int64_t *offs, size_t n, int64_t *out_len, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
@@ -538,8 +628,8 @@ cudaError_t launch_normalise(const uint8_t *res, const int64_t *offs, size_t n, 
                              int64_t *out_offs, int64_t *out_len, void *scan_tmp, cudaStream_t st)
 {
     const size_t nb = norm_blocks(total_bytes);
-    if (strip) nz_count_kernel<true><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, block_counts);
-    else nz_count_kernel<false><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, block_counts);
+    if (strip) nz_count_kernel<true><<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(res, total_bytes, block_counts, nb);
+    else nz_count_kernel<false><<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(res, total_bytes, block_counts, nb);
     {
         cudaError_t es = scan_counts(block_counts, nb, block_prefix, scan_tmp, st);
         if (es != cudaSuccess) return es;

@@ -76,6 +76,9 @@ cudaError_t scan_counts(const uint32_t *counts, size_t n, int64_t *prefix, void 
 // bytes >= 0x80 in res[0, total_bytes) into *count (device memory)
 cudaError_t launch_count_nonascii(const uint8_t *res, size_t total_bytes, unsigned long long *count, cudaStream_t st);
 
+// rapidhash32 digests (4 bytes each) from finished rapidhash digests (8 bytes each): the record is hashed once for both
+cudaError_t launch_rapid_fold32(const uint8_t *h64, size_t n, uint8_t *h32, cudaStream_t st);
+
 cudaError_t launch_lengths(const int64_t *offs, size_t n, int64_t *out_len, cudaStream_t st);
 
 cudaError_t launch_synth_fill(uint8_t *res, size_t total_bytes, uint64_t seed, unsigned lower_permille,

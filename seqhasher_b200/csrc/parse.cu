@@ -18,6 +18,7 @@
 // Formatter.  fmt_len_kernel + scan_counts + fmt_write_kernel build the output of seqhasher.go:261-282
 // (`file;h1;..;hn;Name`, --headersonly, record.Format(0) for FASTA/FASTQ), hex encoding included.
 #include "hash_all.cuh"
+#include "inflate.cuh"
 #include "parse.cuh"
 
 namespace shb {
@@ -488,6 +489,60 @@ __global__ void __launch_bounds__(256) fmt_write_kernel(FmtCfg c, FxOut rec, siz
             o[j] = ch;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------- BGZF inflate
+
+// One warp per BGZF member: lane 0 runs the DEFLATE decoder (inflate.cuh) with its tables in the warp's slice of shared memory
+// and then checks the member's CRC-32 (slice-by-4, tables built per CTA).  Members are independent by construction of the
+// format (each is a complete gzip member of <= 64 KiB of text), so a 64 MiB text chunk is ~1000 warps of work, and the
+// compressed bytes — a third to a quarter of the text — are all that crosses PCIe.
+__global__ void __launch_bounds__(256) bgzf_inflate_kernel(const uint8_t *__restrict__ comp, const unsigned long long *__restrict__ tab,
+                                                           size_t n_members, uint8_t *__restrict__ text,
+                                                           unsigned long long *__restrict__ status)
+{
+    __shared__ InflateScratch s_scr[8];
+    __shared__ uint32_t s_crc[4][256];
+    {
+        const uint32_t i = threadIdx.x;   // 256 threads: one table column each
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+        s_crc[0][i] = c;
+        __syncthreads();
+        uint32_t c1 = s_crc[0][i];
+        for (int t = 1; t < 4; t++) {
+            c1 = s_crc[0][c1 & 0xffu] ^ (c1 >> 8);
+            s_crc[t][i] = c1;
+        }
+        __syncthreads();
+    }
+    const size_t m = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (m >= n_members || (threadIdx.x & 31u) != 0) return;
+    const unsigned long long off = tab[4 * m], clen = tab[4 * m + 1], packed = tab[4 * m + 2], out = tab[4 * m + 3];
+    const uint32_t isize = (uint32_t)packed, want_crc = (uint32_t)(packed >> 32);
+    uint8_t *dst = text + out;
+    int rc = inflate_raw(comp + off, (uint32_t)clen, dst, isize, s_scr[threadIdx.x >> 5]);
+    if (rc == INF_OK) {
+        uint32_t c = 0xffffffffu, k = 0;
+        for (; k < isize && ((uintptr_t)(dst + k) & 3u); k++) c = s_crc[0][(c ^ dst[k]) & 0xffu] ^ (c >> 8);
+        for (; k + 4 <= isize; k += 4) {
+            c ^= *reinterpret_cast<const uint32_t *>(dst + k);
+            c = s_crc[3][c & 0xffu] ^ s_crc[2][(c >> 8) & 0xffu] ^ s_crc[1][(c >> 16) & 0xffu] ^ s_crc[0][c >> 24];
+        }
+        for (; k < isize; k++) c = s_crc[0][(c ^ dst[k]) & 0xffu] ^ (c >> 8);
+        if ((c ^ 0xffffffffu) != want_crc) rc = 100;
+    }
+    if (rc != INF_OK) atomicMin(status, (unsigned long long)m + 1ull);
+}
+
+cudaError_t launch_bgzf_inflate(const uint8_t *comp, const unsigned long long *tab, size_t n_members, uint8_t *text,
+                                unsigned long long *status, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(status, 0xff, sizeof(unsigned long long), st);   // "no failure" = the largest value (atomicMin)
+    if (e != cudaSuccess || n_members == 0) return e;
+    bgzf_inflate_kernel<<<(unsigned)((n_members + 7) / 8), 256, 0, st>>>(comp, tab, n_members, text, status);
+    g_launches++;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------- launchers

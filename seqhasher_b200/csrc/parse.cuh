@@ -46,6 +46,12 @@ struct FmtCfg {
     int headers_only, fastq, upper;
 };
 
+// BGZF members inflated on the device (inflate.cuh): member i = deflate data comp[tab[4i], +tab[4i+1]) -> text[tab[4i+3], +isize),
+// tab[4i+2] = isize | crc32 << 32.  *status receives 0, or 1 + the index of the first member that failed to decode, did not
+// produce isize bytes or whose CRC-32 differs.
+cudaError_t launch_bgzf_inflate(const uint8_t *comp, const unsigned long long *tab, size_t n_members, uint8_t *text,
+                                unsigned long long *status, cudaStream_t st);
+
 size_t fx_scratch_bytes(size_t n_bytes);
 cudaError_t launch_fx_parse(const uint8_t *text, size_t n, bool fastq, bool is_final, FxOut out, FxInfo *info,
                             void *scratch, cudaStream_t st);

@@ -49,8 +49,22 @@ __device__ __forceinline__ void hash_set(const R &r, uint32_t len, size_t i, con
     hash_if<MASK, A_NTHASH, NT_SWZ>(r, len, i, out, rmask, nt_lut);
     hash_if<MASK, A_BLAKE3, NT_SWZ>(r, len, i, out, rmask, nt_lut);
     hash_if<MASK, A_K12, NT_SWZ>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_RAPIDHASH, NT_SWZ>(r, len, i, out, rmask, nt_lut);
-    hash_if<MASK, A_RAPIDHASH32, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    // rapidhash32 is a fold of rapidhash (seqhasher.go:340-343): when both are asked for the record is hashed once
+    constexpr uint32_t RAPID_BOTH = (1u << A_RAPIDHASH) | (1u << A_RAPIDHASH32);
+    if ((MASK & RAPID_BOTH) == RAPID_BOTH && (rmask & RAPID_BOTH) == RAPID_BOTH) {
+        uint8_t *o64 = out.p[A_RAPIDHASH] + i * 8, *o32 = out.p[A_RAPIDHASH32] + i * 4;
+        if (len == 0) {
+            zero_digest<A_RAPIDHASH>(o64);
+            zero_digest<A_RAPIDHASH32>(o32);
+        } else {
+            const uint64_t h = rapidhash_record(r, len);
+            store_be64(o64, h);
+            *reinterpret_cast<uint32_t *>(o32) = bswap32((uint32_t)h ^ (uint32_t)(h >> 32));
+        }
+    } else {
+        hash_if<MASK, A_RAPIDHASH, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+        hash_if<MASK, A_RAPIDHASH32, NT_SWZ>(r, len, i, out, rmask, nt_lut);
+    }
 }
 
 constexpr uint32_t TMA_CHUNK = 32768;   // one bulk copy moves at most this many bytes

@@ -52,6 +52,11 @@ def main():
         res = al[rng.integers(0, len(al), size=int(offs[-1]))] if offs[-1] else np.zeros(0, np.uint8)
         k = int(rng.integers(1, 5))
         algos = [B.ALGO_NAMES[i] for i in rng.choice(12, size=k, replace=bool(rng.integers(2)) and k > 1)]
+        pick = rng.random()
+        if pick < 0.15:
+            algos = ["xxhash", "xxh3", "murmur3"]          # the fused one-pass set of config C3 (hash_fused3.cuh)
+        elif pick < 0.25:
+            algos = ["blake3", "nthash"] + ([B.ALGO_NAMES[int(rng.integers(12))]] if rng.random() < 0.3 else [])   # C4: one pass on long records
         flags = int(rng.integers(0, 4)) | extra_flags[rng.integers(len(extra_flags))]
         got, glen = B.hash_batch(res, offs, algos, flags)
         want, wlen = O.batch(res, offs, algos, flags & 3, threads=8)
