@@ -68,6 +68,10 @@ enum shb_algo {
  * reference's reader yields those before it fails (seqhasher.go:228-239) — and the host then reports
  * "Error reading record: fastx: invalid FASTA/Q format". */
 #define SHB_PARTIAL_FORMAT 1
+#define SHB_ERR_INFLATE (-7)     /* a BGZF member does not decode, or its ISIZE / CRC-32 differs ("flate: corrupt input", "gzip: invalid checksum") */
+/* shb_textproc_run_bgzf only (> 0): the record that crosses the end of the chunk's own members does not end inside the extra
+ * members; nothing was produced, the host stages more extra members and calls again. */
+#define SHB_NEED_MORE 2
 
 /* Library lifetime.  n_gpus <= 0 uses every visible device; devices 0..n-1 otherwise.  Returns the
  * number of devices in use (>0) or an error.  Idempotent. */
@@ -169,8 +173,40 @@ size_t shb_textproc_empty_records(shb_textproc *t);
 /* sequence bytes >= 0x80 seen in the last chunk (whole chunk, also its unconsumed tail): not 0 means the output may differ
  * from the reference's, which normalises such records with Unicode rules (seqhasher.go:243-251); the hosts refuse the input */
 size_t shb_textproc_nonascii(shb_textproc *t);
-/* device time of the last run, ms: H2D copy, record split, hashes, formatting (incl. its host syncs), D2H copy */
+/* device time of the last run, ms: H2D copy (BGZF: + inflate and boundary search), record split, hashes, formatting (incl. its
+ * host syncs), D2H copy */
 void shb_textproc_last_ms(shb_textproc *t, float *ms5);
+
+/* ---- the same loop for BGZF input (bgzip / htslib blocked gzip): the members are inflated ON THE DEVICE ----
+ *
+ * Replaces xopen's gzip reader in front of the record loop (seqhasher.go:210-226 -> pgzip, go.mod:20-31) for the one gzip
+ * container whose members the host can delimit without decoding: every BGZF member carries its compressed size in a 'BC' extra
+ * field and holds at most 64 KiB of text.  Only compressed bytes cross PCIe; one warp inflates one member (ISIZE and CRC-32
+ * verified) into the text buffer the splitter reads.  Any other gzip stream stays with the host feeder.
+ *
+ * The host cuts the member sequence into chunks wherever it likes.  A chunk = n_own members it owns + n_extra members that
+ * follow them (look-ahead for the record that crosses the chunk's end).  The chunk's records are those that START after its
+ * first text byte and not after the first byte behind its own members; the chunk that begins the input passes first_start =
+ * text offset of the first non-blank byte (the host sniffs the format there by inflating the first member itself), every other
+ * chunk passes -1.  at_eof = the last extra (or own) member is the last of the input.  Chunks are independent: any order, any
+ * number in flight, any GPU.
+ *   shb_textproc_bgzf_input: pinned staging for the members' bytes (grown on demand, contents kept); NULL on failure.
+ *   members: 3 words per member: offset of the raw DEFLATE data in the staging buffer (behind the member's header), its
+ *            length, ISIZE | CRC32 << 32 (the member's trailer).
+ * Returns SHB_OK (output / consumed / records / ... as after shb_textproc_run), SHB_PARTIAL_FORMAT, SHB_NEED_MORE, or < 0
+ * (SHB_ERR_INFLATE for damaged members, SHB_ERR_CAPACITY when the members' text exceeds shb_textproc_capacity()).
+ * When the record index fills up (consumed < the chunk's text, SHB_OK), shb_textproc_resume runs the rest of the
+ * device-resident text; repeat until shb_textproc_records() == 0 or everything is consumed. */
+uint8_t *shb_textproc_bgzf_input(shb_textproc *t, size_t comp_capacity);
+int shb_textproc_run_bgzf(shb_textproc *t, size_t n_comp_bytes, const uint64_t *members, size_t n_own, size_t n_extra,
+                          long long first_start, int at_eof, int format, const int *algos, int n_algos,
+                          unsigned flags, int headers_only, const char *label);
+int shb_textproc_resume(shb_textproc *t, int format, const int *algos, int n_algos, unsigned flags, int headers_only,
+                        const char *label);
+/* device time of the inflate kernel of the last shb_textproc_run_bgzf, ms (part of the first entry of shb_textproc_last_ms) */
+float shb_textproc_last_inflate_ms(shb_textproc *t);
+/* 1 when the last device-resident chunk has text left for shb_textproc_resume */
+int shb_textproc_pending(shb_textproc *t);
 
 /* ---- measurement helpers (not part of the hashing path) ---- */
 

@@ -35,8 +35,11 @@ EXPORTS = [
     "shb_probe_int_peak", "shb_probe_last_checksum", "shb_probe_h2d", "shb_debug_oob", "shb_textproc_create", "shb_textproc_destroy",
     "shb_textproc_input", "shb_textproc_capacity", "shb_textproc_run", "shb_textproc_output", "shb_textproc_consumed",
     "shb_textproc_records", "shb_textproc_empty_records", "shb_textproc_last_ms",
+    "shb_textproc_bgzf_input", "shb_textproc_run_bgzf", "shb_textproc_resume", "shb_textproc_pending", "shb_textproc_last_inflate_ms",
 ]
 PARTIAL_FORMAT = 1   # shb_textproc_run: SHB_PARTIAL_FORMAT
+NEED_MORE = 2        # shb_textproc_run_bgzf: SHB_NEED_MORE
+ERR_INFLATE = -7
 FORMAT_FASTA = 1
 FORMAT_FASTQ = 2
 
@@ -96,6 +99,14 @@ def lib() -> ctypes.CDLL:
     L.shb_textproc_run.argtypes = [c.c_void_p, c.c_size_t, c.c_int, c.c_int, c.POINTER(c.c_int), c.c_int, c.c_uint, c.c_int,
                                    c.c_char_p]
     L.shb_textproc_run.restype = c.c_int
+    L.shb_textproc_bgzf_input.argtypes = [c.c_void_p, c.c_size_t]; L.shb_textproc_bgzf_input.restype = c.c_void_p
+    L.shb_textproc_run_bgzf.argtypes = [c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_size_t, c.c_longlong, c.c_int, c.c_int,
+                                        c.POINTER(c.c_int), c.c_int, c.c_uint, c.c_int, c.c_char_p]
+    L.shb_textproc_run_bgzf.restype = c.c_int
+    L.shb_textproc_resume.argtypes = [c.c_void_p, c.c_int, c.POINTER(c.c_int), c.c_int, c.c_uint, c.c_int, c.c_char_p]
+    L.shb_textproc_resume.restype = c.c_int
+    L.shb_textproc_pending.argtypes = [c.c_void_p]; L.shb_textproc_pending.restype = c.c_int
+    L.shb_textproc_last_inflate_ms.argtypes = [c.c_void_p]; L.shb_textproc_last_inflate_ms.restype = c.c_float
     L.shb_textproc_output.argtypes = [c.c_void_p, c.POINTER(c.c_size_t)]; L.shb_textproc_output.restype = c.c_void_p
     L.shb_textproc_last_ms.argtypes = [c.c_void_p, c.POINTER(c.c_float)]; L.shb_textproc_last_ms.restype = None
     for nm in ("shb_textproc_consumed", "shb_textproc_records", "shb_textproc_empty_records"):
@@ -301,6 +312,52 @@ class TextProc:
         # zero-copy view of the pinned output buffer (valid until the next run)
         out = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(nb.value,)) if nb.value else np.zeros(0, np.uint8)
         return out, L.shb_textproc_consumed(self._h), L.shb_textproc_records(self._h), L.shb_textproc_empty_records(self._h)
+
+    def _results(self, rc: int):
+        L = lib()
+        self.nonascii = L.shb_textproc_nonascii(self._h)
+        self.partial_format = rc == PARTIAL_FORMAT
+        nb = ctypes.c_size_t(0)
+        p = L.shb_textproc_output(self._h, ctypes.byref(nb))
+        out = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(nb.value,)) if nb.value else np.zeros(0, np.uint8)
+        return out, L.shb_textproc_consumed(self._h), L.shb_textproc_records(self._h), L.shb_textproc_empty_records(self._h)
+
+    def bgzf_input(self, comp_capacity: int) -> np.ndarray:
+        """Pinned staging for the bytes of BGZF members (shb_textproc_bgzf_input), at least comp_capacity bytes."""
+        p = lib().shb_textproc_bgzf_input(self._h, comp_capacity)
+        if not p:
+            raise SeqhashError(f"shb_textproc_bgzf_input failed: {lib().shb_last_error().decode()}")
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(comp_capacity,))
+
+    def run_bgzf(self, n_comp_bytes: int, members: np.ndarray, n_own: int, n_extra: int, first_start: int, at_eof: bool,
+                 fmt: int, algos, flags: int, headers_only: bool, label: bytes | None):
+        """shb_textproc_run_bgzf: members = uint64 array (n_own + n_extra, 3): offset of the raw DEFLATE data in the staging
+        buffer, its length, ISIZE | CRC32 << 32.  Returns None for SHB_NEED_MORE (stage more extra members and call again),
+        else (output view, consumed, n_records, n_empty); the rest of a partly consumed chunk (self.pending()) goes through
+        resume()."""
+        ids = list(algos)
+        arr = (ctypes.c_int * max(len(ids), 1))(*ids)
+        m = np.ascontiguousarray(members, dtype=np.uint64).reshape(-1, 3)
+        assert len(m) == n_own + n_extra
+        rc = lib().shb_textproc_run_bgzf(self._h, n_comp_bytes, m.ctypes.data if len(m) else None, n_own, n_extra, first_start,
+                                         1 if at_eof else 0, fmt, arr, len(ids), flags, 1 if headers_only else 0, label)
+        _check(rc, "shb_textproc_run_bgzf")
+        if rc == NEED_MORE:
+            return None
+        return self._results(rc)
+
+    def last_inflate_ms(self) -> float:
+        return float(lib().shb_textproc_last_inflate_ms(self._h))
+
+    def pending(self) -> bool:
+        return bool(lib().shb_textproc_pending(self._h))
+
+    def resume(self, fmt: int, algos, flags: int, headers_only: bool, label: bytes | None):
+        ids = list(algos)
+        arr = (ctypes.c_int * max(len(ids), 1))(*ids)
+        rc = lib().shb_textproc_resume(self._h, fmt, arr, len(ids), flags, 1 if headers_only else 0, label)
+        _check(rc, "shb_textproc_resume")
+        return self._results(rc)
 
     def last_ms(self) -> dict:
         arr = (ctypes.c_float * 5)()

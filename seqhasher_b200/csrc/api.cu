@@ -568,6 +568,14 @@ struct shb_textproc {
     size_t scratch_cap = 0;
     uint8_t *d_out = nullptr, *h_out = nullptr;
     size_t out_cap = 0;
+    // BGZF input (allocated on first use): pinned + device staging of the compressed members, their table, the inflated text
+    uint8_t *h_comp = nullptr, *d_comp = nullptr, *d_stage = nullptr;
+    size_t comp_cap = 0, tab_cap = 0;
+    unsigned long long *h_tab = nullptr, *d_tab = nullptr;
+    long long *d_bounds = nullptr, *h_bounds = nullptr;   // 4 results of fx_bounds_kernel + the inflate status
+    size_t dev_text_bytes = 0;                            // bytes of d_text a device-resident run worked on (shb_textproc_resume)
+    cudaEvent_t ev_inf[2] = {};                           // around the inflate kernel
+    float inflate_ms = 0.f;
     // results of the last run
     size_t out_bytes = 0, consumed = 0, n_records = 0, n_empty = 0, n_nonascii = 0;
     cudaEvent_t ev[6] = {};     // start, after H2D, after split, after hash, after format, after D2H
@@ -617,37 +625,26 @@ void shb_textproc_destroy(shb_textproc *t)
     cudaSetDevice(t->device);
     if (t->stream) { cudaStreamSynchronize(t->stream); cudaStreamDestroy(t->stream); }
     for (int k = 0; k < 6; k++) if (t->ev[k]) cudaEventDestroy(t->ev[k]);
+    for (int k = 0; k < 2; k++) if (t->ev_inf[k]) cudaEventDestroy(t->ev_inf[k]);
     cudaFreeHost(t->h_text); cudaFreeHost(t->h_info); cudaFreeHost(t->h_out);
     cudaFree(t->d_text); cudaFree(t->d_res); cudaFree(t->d_parse_scratch); cudaFree(t->d_info);
     cudaFree(t->rec.offsets); cudaFree(t->rec.name_start); cudaFree(t->rec.name_len); cudaFree(t->rec.qual_start);
     cudaFree(t->rec.qual_len); cudaFree(t->rec.rec_start); cudaFree(t->d_out_len); cudaFree(t->d_out_off);
     cudaFree(t->d_label); cudaFree(t->d_fmt_scan); cudaFree(t->d_dig); cudaFree(t->d_scratch); cudaFree(t->d_out);
+    cudaFreeHost(t->h_comp); cudaFreeHost(t->h_tab); cudaFreeHost(t->h_bounds);
+    cudaFree(t->d_comp); cudaFree(t->d_stage); cudaFree(t->d_tab); cudaFree(t->d_bounds);
     delete t;
 }
 
 uint8_t *shb_textproc_input(shb_textproc *t) { return t ? t->h_text : nullptr; }
 size_t shb_textproc_capacity(shb_textproc *t) { return t ? t->cap : 0; }
 
-int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, const int *algos, int n_algos,
-                     unsigned flags, int headers_only, const char *label)
+// The record loop on a text that is already in t->d_text (16 zero bytes behind it): split, hash, format, copy the output back.
+// ev[0] / ev[1] have been recorded by the caller around whatever brought the text there.
+static int textproc_process(shb_textproc *t, size_t n_bytes, int format, int is_final, const int *algos, int n_algos,
+                            unsigned flags, int headers_only, const char *label, size_t label_len)
 {
-    if (!t) return fail(SHB_ERR_BAD_ARG, "null textproc");
-    if (int rc = check_algos(algos, n_algos)) return rc;
-    if (n_algos > shb::FMT_MAX_FIELDS) return fail(SHB_ERR_BAD_ARG, "too many hash types (at most 48 fields per record)");
-    if (n_bytes > t->cap) return fail(SHB_ERR_CAPACITY, "text larger than the textproc capacity");
-    if (format != SHB_FORMAT_FASTA && format != SHB_FORMAT_FASTQ) return fail(SHB_ERR_BAD_ARG, "format must be FASTA or FASTQ");
-    const size_t label_len = label ? std::strlen(label) : 0;
-    if (label_len > 4096) return fail(SHB_ERR_BAD_ARG, "label too long");
-    CU(cudaSetDevice(t->device));
-    t->out_bytes = t->consumed = t->n_records = t->n_empty = t->n_nonascii = 0;
-    if (n_bytes == 0) return SHB_OK;
-    if (is_final && t->h_text[n_bytes - 1] != '\n') t->h_text[n_bytes++] = '\n';   // the pinned buffer has 64 spare bytes
-    std::memset(t->h_text + n_bytes, 0, 32);
     cudaStream_t st = t->stream;
-    for (float &m : t->ms) m = 0.f;
-    CU(cudaEventRecord(t->ev[0], st));
-    CU(cudaMemcpyAsync(t->d_text, t->h_text, align_up(n_bytes + 16, 16), cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(t->ev[1], st));
     if (label_len) CU(cudaMemcpyAsync(t->d_label, label, label_len, cudaMemcpyHostToDevice, st));
     // 1. split into records (CSR residues + name / quality spans)
     CU(shb::launch_fx_parse(t->d_text, n_bytes, format == SHB_FORMAT_FASTQ, is_final != 0, t->rec, t->d_info, t->d_parse_scratch, st));
@@ -717,6 +714,177 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
     for (int k = 0; k < 5; k++) cudaEventElapsedTime(&t->ms[k], t->ev[k], t->ev[k + 1]);
     t->out_bytes = out_bytes;
     return done_rc;
+}
+
+static int textproc_check_args(shb_textproc *t, int format, const int *algos, int n_algos, const char *label, size_t *label_len)
+{
+    if (!t) return fail(SHB_ERR_BAD_ARG, "null textproc");
+    if (int rc = check_algos(algos, n_algos)) return rc;
+    if (n_algos > shb::FMT_MAX_FIELDS) return fail(SHB_ERR_BAD_ARG, "too many hash types (at most 48 fields per record)");
+    if (format != SHB_FORMAT_FASTA && format != SHB_FORMAT_FASTQ) return fail(SHB_ERR_BAD_ARG, "format must be FASTA or FASTQ");
+    *label_len = label ? std::strlen(label) : 0;
+    if (*label_len > 4096) return fail(SHB_ERR_BAD_ARG, "label too long");
+    return SHB_OK;
+}
+
+int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, const int *algos, int n_algos,
+                     unsigned flags, int headers_only, const char *label)
+{
+    size_t label_len = 0;
+    if (int rc = textproc_check_args(t, format, algos, n_algos, label, &label_len)) return rc;
+    if (n_bytes > t->cap) return fail(SHB_ERR_CAPACITY, "text larger than the textproc capacity");
+    CU(cudaSetDevice(t->device));
+    t->out_bytes = t->consumed = t->n_records = t->n_empty = t->n_nonascii = 0;
+    t->dev_text_bytes = 0;
+    if (n_bytes == 0) return SHB_OK;
+    if (is_final && t->h_text[n_bytes - 1] != '\n') t->h_text[n_bytes++] = '\n';   // the pinned buffer has 64 spare bytes
+    std::memset(t->h_text + n_bytes, 0, 32);
+    cudaStream_t st = t->stream;
+    for (float &m : t->ms) m = 0.f;
+    CU(cudaEventRecord(t->ev[0], st));
+    CU(cudaMemcpyAsync(t->d_text, t->h_text, align_up(n_bytes + 16, 16), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(t->ev[1], st));
+    return textproc_process(t, n_bytes, format, is_final, algos, n_algos, flags, headers_only, label, label_len);
+}
+
+// ---- BGZF input: compressed members in, the same output out; the text exists on the device only ----
+
+uint8_t *shb_textproc_bgzf_input(shb_textproc *t, size_t comp_capacity)
+{
+    if (!t) { fail(SHB_ERR_BAD_ARG, "null textproc"); return nullptr; }
+    if (comp_capacity <= t->comp_cap) return t->h_comp;
+    if (cudaSetDevice(t->device) != cudaSuccess) { fail(SHB_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+    cudaStreamSynchronize(t->stream);
+    uint8_t *nh = nullptr, *nd = nullptr;
+    if (cudaHostAlloc(&nh, comp_capacity + 64, cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&nd, comp_capacity + 64) != cudaSuccess) {
+        cudaFreeHost(nh);
+        fail(SHB_ERR_CUDA, std::string("BGZF staging allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    if (t->h_comp && t->comp_cap) std::memcpy(nh, t->h_comp, t->comp_cap);   // growing keeps what the caller has staged
+    cudaFreeHost(t->h_comp); cudaFree(t->d_comp);
+    t->h_comp = nh; t->d_comp = nd; t->comp_cap = comp_capacity;
+    return t->h_comp;
+}
+
+int shb_textproc_run_bgzf(shb_textproc *t, size_t n_comp_bytes, const uint64_t *members, size_t n_own, size_t n_extra,
+                          long long first_start, int at_eof, int format, const int *algos, int n_algos,
+                          unsigned flags, int headers_only, const char *label)
+{
+    size_t label_len = 0;
+    if (int rc = textproc_check_args(t, format, algos, n_algos, label, &label_len)) return rc;
+    if (n_comp_bytes > t->comp_cap || !t->h_comp) return fail(SHB_ERR_CAPACITY, "more compressed bytes than shb_textproc_bgzf_input was asked for");
+    const size_t nm = n_own + n_extra;
+    if (nm && !members) return fail(SHB_ERR_BAD_ARG, "null member table");
+    CU(cudaSetDevice(t->device));
+    t->out_bytes = t->consumed = t->n_records = t->n_empty = t->n_nonascii = 0;
+    t->dev_text_bytes = 0;
+    if (nm == 0) return SHB_OK;
+    if (!t->d_stage) {
+        CU(cudaMalloc(&t->d_stage, t->cap + 64));
+        CU(cudaMalloc(&t->d_bounds, 8 * sizeof(long long)));
+        CU(cudaHostAlloc(&t->h_bounds, 8 * sizeof(long long), cudaHostAllocDefault));
+        CU(cudaEventCreate(&t->ev_inf[0]));
+        CU(cudaEventCreate(&t->ev_inf[1]));
+    }
+    if (nm > t->tab_cap) {
+        cudaStreamSynchronize(t->stream);
+        cudaFreeHost(t->h_tab); cudaFree(t->d_tab);
+        t->h_tab = nullptr; t->d_tab = nullptr; t->tab_cap = 0;
+        const size_t want = nm + nm / 2 + 1024;
+        CU(cudaHostAlloc(&t->h_tab, want * 32, cudaHostAllocDefault));
+        CU(cudaMalloc(&t->d_tab, want * 32));
+        t->tab_cap = want;
+    }
+    // the library's table: where every member's text goes (prefix sum of ISIZE)
+    size_t text_bytes = 0, own_bytes = 0;
+    for (size_t i = 0; i < nm; i++) {
+        const uint64_t off = members[3 * i], clen = members[3 * i + 1], packed = members[3 * i + 2];
+        const uint32_t isize = (uint32_t)packed;
+        if (off > n_comp_bytes || clen > n_comp_bytes - off) return fail(SHB_ERR_BAD_ARG, "BGZF member outside the staged bytes");
+        if (isize > 65536u) return fail(SHB_ERR_BAD_ARG, "BGZF member announces more than 64 KiB of text");
+        t->h_tab[4 * i] = off; t->h_tab[4 * i + 1] = clen; t->h_tab[4 * i + 2] = packed; t->h_tab[4 * i + 3] = text_bytes;
+        text_bytes += isize;
+        if (i + 1 == n_own) own_bytes = text_bytes;
+    }
+    if (text_bytes + 1 > t->cap) return fail(SHB_ERR_CAPACITY, "text larger than the textproc capacity");
+    cudaStream_t st = t->stream;
+    for (float &m : t->ms) m = 0.f;
+    CU(cudaEventRecord(t->ev[0], st));
+    CU(cudaMemcpyAsync(t->d_comp, t->h_comp, align_up(n_comp_bytes + 16, 16), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(t->d_tab, t->h_tab, nm * 32, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(t->ev_inf[0], st));
+    CU(shb::launch_bgzf_inflate(t->d_comp, t->d_tab, nm, t->d_stage, reinterpret_cast<unsigned long long *>(t->d_bounds + 4), st));
+    CU(cudaEventRecord(t->ev_inf[1], st));
+    // Which records are this chunk's: the record starts p with 0 < p <= own_bytes, p counted from the chunk's first text byte
+    // (the first chunk of the input also owns p = first_start).  The next chunk looks for its first record start from ITS
+    // byte 1 on, which is this chunk's own_bytes + 1: both derive the shared boundary from the same bytes with the same rule,
+    // so no record is lost or taken twice.
+    const long long from0 = first_start >= 0 ? first_start : 1;
+    const long long from1 = (long long)own_bytes + 1;
+    CU(shb::launch_fx_bounds(t->d_stage, text_bytes, first_start >= 0 ? -1 : from0, from1, format == SHB_FORMAT_FASTQ, t->d_bounds, st));
+    CU(cudaMemcpyAsync(t->h_bounds, t->d_bounds, 5 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&t->inflate_ms, t->ev_inf[0], t->ev_inf[1]);
+    const unsigned long long inf_status = (unsigned long long)t->h_bounds[4];
+    if (inf_status != ~0ull) {
+        const unsigned code = (unsigned)(inf_status & 0xffu);
+        return fail(SHB_ERR_INFLATE, code == 9u ? "gzip: invalid checksum" : "flate: corrupt input");
+    }
+    long long start = first_start >= 0 ? first_start : t->h_bounds[0];
+    long long end = t->h_bounds[1];
+    const long long trimmed = t->h_bounds[2];
+    int is_final = 0;
+    if (end < 0) {
+        if (!at_eof) return SHB_NEED_MORE;          // the record that crosses the chunk's end is longer than the extra members
+        end = trimmed;                               // the input ends inside (or right behind) this chunk's last record
+        is_final = 1;
+    }
+    if (start < 0 || start >= end) {                 // no record starts in this chunk (one long record runs through it)
+        t->consumed = 0;
+        for (int k = 0; k < 5; k++) t->ms[k] = 0.f;
+        return SHB_OK;
+    }
+    size_t n_bytes = (size_t)(end - start);
+    CU(cudaMemcpyAsync(t->d_text, t->d_stage + start, n_bytes, cudaMemcpyDeviceToDevice, st));
+    bool add_nl = false;
+    if (is_final) {
+        // a missing last line break is added (the reader's rule for the end of the input)
+        if ((size_t)end < text_bytes) add_nl = true;                       // blanks were trimmed: whatever followed, the line ends here
+        else add_nl = (uint8_t)t->h_bounds[3] != '\n';
+    }
+    if (add_nl) { CU(cudaMemsetAsync(t->d_text + n_bytes, '\n', 1, st)); n_bytes++; }
+    CU(cudaMemsetAsync(t->d_text + n_bytes, 0, 32, st));
+    CU(cudaEventRecord(t->ev[1], st));
+    t->dev_text_bytes = n_bytes;
+    // every chunk holds whole records only, so each is "final" for the splitter
+    return textproc_process(t, n_bytes, format, 1, algos, n_algos, flags, headers_only, label, label_len);
+}
+
+int shb_textproc_resume(shb_textproc *t, int format, const int *algos, int n_algos, unsigned flags, int headers_only, const char *label)
+{
+    size_t label_len = 0;
+    if (int rc = textproc_check_args(t, format, algos, n_algos, label, &label_len)) return rc;
+    if (!t->d_stage || t->dev_text_bytes == 0 || t->consumed == 0 || t->consumed >= t->dev_text_bytes)
+        return fail(SHB_ERR_BAD_ARG, "nothing to resume: the last run was not a partly consumed device-resident chunk");
+    CU(cudaSetDevice(t->device));
+    cudaStream_t st = t->stream;
+    const size_t rest = t->dev_text_bytes - t->consumed;
+    CU(cudaEventRecord(t->ev[0], st));
+    CU(cudaMemcpyAsync(t->d_stage, t->d_text + t->consumed, rest, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(t->d_text, t->d_stage, rest, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(t->d_text + rest, 0, 32, st));
+    CU(cudaEventRecord(t->ev[1], st));
+    t->out_bytes = t->consumed = t->n_records = t->n_empty = t->n_nonascii = 0;
+    t->dev_text_bytes = rest;
+    return textproc_process(t, rest, format, 1, algos, n_algos, flags, headers_only, label, label_len);
+}
+
+float shb_textproc_last_inflate_ms(shb_textproc *t) { return t ? t->inflate_ms : 0.f; }
+
+int shb_textproc_pending(shb_textproc *t)
+{
+    return t && t->dev_text_bytes && t->n_records && t->consumed && t->consumed < t->dev_text_bytes ? 1 : 0;
 }
 
 const uint8_t *shb_textproc_output(shb_textproc *t, size_t *out_bytes)

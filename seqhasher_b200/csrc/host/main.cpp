@@ -10,12 +10,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -541,7 +543,11 @@ size_t pread_full(int fd, uint8_t *dst, size_t n, size_t off)
     return got;
 }
 
-void range_worker(RangeSlot *s, const RunArgs *a, const RangeJob *job, size_t cap0)
+// what a slot does with chunk `seq`: returns the rc of the last run; fills s->acc (output of all runs but the last, which stays
+// in s->tp), s->err and the counters
+using ChunkFn = std::function<int(RangeSlot *, long long)>;
+
+void slot_thread(RangeSlot *s, size_t cap0, const ChunkFn *fn)
 {
     // the slot's textproc is created here, on its own thread: the CUDA contexts of several devices come up side by side
     s->tp = shb_textproc_create(s->device, cap0);
@@ -557,10 +563,25 @@ void range_worker(RangeSlot *s, const RunArgs *a, const RangeJob *job, size_t ca
         }
         s->acc.clear();
         s->n_empty = s->n_nonascii = 0;
-        int rc = 0;
-        if (!s->tp) {
-            rc = -1;
-        } else {
+        int rc = -1;
+        if (s->tp) {
+            s->err.clear();
+            rc = (*fn)(s, seq);
+        }
+        s->rc = rc;
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            s->done = seq;
+        }
+        s->cv.notify_all();
+    }
+}
+
+int range_chunk(RangeSlot *s, long long seq, const RunArgs *a, const RangeJob *job)
+{
+    int rc = 0;
+    {
+        {
             s->err.clear();
             const size_t lo_nom = job->first + (size_t)seq * job->C;
             const size_t hi_nom = std::min(job->file_size, lo_nom + job->C);
@@ -630,14 +651,11 @@ void range_worker(RangeSlot *s, const RunArgs *a, const RangeJob *job, size_t ca
                 shb_textproc_run(s->tp, 0, a->format, 1, nullptr, 0, a->flags, a->headers_only, a->label);   // clears the last output
             }
         }
-        s->rc = rc;
-        {
-            std::lock_guard<std::mutex> lk(s->mu);
-            s->done = seq;
-        }
-        s->cv.notify_all();
     }
+    return rc;
 }
+
+int run_chunk_slots(long long nchunks, int n_gpus, size_t cap0, const ChunkFn &fn, FILE *out, const RunArgs &args, std::string &err);
 
 int process_file_ranges(int fd, size_t file_size, FILE *out, const Config &cfg, int n_gpus, std::string &err)
 {
@@ -681,19 +699,25 @@ int process_file_ranges(int fd, size_t file_size, FILE *out, const Config &cfg, 
         else { err = "Failed to create reader: fastx: invalid FASTA/Q format"; return 1; }
     }
     const long long nchunks = (long long)((file_size - job.first + job.C - 1) / job.C);
+    const ChunkFn fn = [&](RangeSlot *s, long long seq) { return range_chunk(s, seq, &args, &job); };
+    return run_chunk_slots(nchunks, n_gpus, job.C + job.C / 4 + 4096, fn, out, args, err);
+}
+
+// Chunks 0..nchunks-1 dealt round-robin to K slots (each a thread + a textproc), their outputs written in chunk order.
+int run_chunk_slots(long long nchunks, int n_gpus, size_t cap0, const ChunkFn &fn, FILE *out, const RunArgs &args, std::string &err)
+{
     // Slots: a slot's pread is one thread copying out of the page cache (5-6 GB/s) and a B200 takes ~13 GB/s of text, so one
     // GPU gets four; with more GPUs two each are enough readers, and every slot costs ~0.1 s to set up (80 MB of pinned
     // memory, ~0.5 GB of device buffers) — 32 slots on an 8-GPU box delayed the first chunk by 2.6 s.
     int per_gpu = n_gpus == 1 ? 4 : 2;
     if (const char *e = getenv("SHB_SLOTS_PER_GPU")) { const int v = atoi(e); if (v >= 1 && v <= 16) per_gpu = v; }
-    const int K = (int)std::min<long long>((long long)per_gpu * n_gpus, nchunks);
+    const int K = (int)std::max<long long>(1, std::min<long long>((long long)per_gpu * n_gpus, nchunks));
     phase("before create");
     std::vector<std::unique_ptr<RangeSlot>> slots;
-    const size_t cap0 = job.C + job.C / 4 + 4096;
     for (int k = 0; k < K; k++) {
         slots.emplace_back(new RangeSlot());
         slots[k]->device = k % n_gpus;
-        slots[k]->worker = std::thread(range_worker, slots[k].get(), &args, &job, cap0);
+        slots[k]->worker = std::thread(slot_thread, slots[k].get(), cap0, &fn);
     }
     std::mutex wmu;
     std::condition_variable wcv;
@@ -784,6 +808,196 @@ int process_file_ranges(int fd, size_t file_size, FILE *out, const Config &cfg, 
     return rc;
 }
 
+// ---- BGZF files (bgzip, htslib): the members go to the GPU compressed and are inflated there ----
+//
+// The reference reads .gz through xopen -> pgzip on one goroutine (go.mod:20-31).  Blocked gzip is the one gzip container the
+// host can cut without decoding: every member announces its size in a 'BC' extra field and holds <= 64 KiB of text.  The host
+// walks the member headers once (mmap, two pages touched per member), groups the members into chunks of ~64 MiB of text, and
+// every chunk slot preads its members' bytes into pinned memory and calls shb_textproc_run_bgzf: one warp inflates one member
+// (csrc/inflate.cuh), the splitter runs on the inflated text, and a third to a quarter of the bytes cross PCIe.  A file that
+// is not BGZF from its first byte to its last takes the host-side inflate (pgzip.hpp) as before.
+
+struct BgzfMember {
+    uint64_t start, data, clen, packed;   // first byte of the member, first byte and length of its DEFLATE data, ISIZE | CRC32 << 32
+};
+
+// every member of the file, or false when the bytes are not BGZF throughout (same rules as host/bgzf.py scan_members)
+bool scan_bgzf(const uint8_t *b, size_t n, std::vector<BgzfMember> &out)
+{
+    size_t p = 0;
+    while (p < n) {
+        if (n - p < 18 + 8 || b[p] != 0x1f || b[p + 1] != 0x8b || b[p + 2] != 8 || b[p + 3] != 4) return false;
+        const size_t xlen = b[p + 10] | ((size_t)b[p + 11] << 8);
+        size_t q = p + 12;
+        const size_t xend = q + xlen;
+        if (xend > n) return false;
+        long bsize = -1;
+        while (q + 4 <= xend) {
+            const size_t slen = b[q + 2] | ((size_t)b[q + 3] << 8);
+            if (b[q] == 'B' && b[q + 1] == 'C' && slen == 2 && q + 6 <= xend) bsize = b[q + 4] | ((long)b[q + 5] << 8);
+            q += 4 + slen;
+        }
+        if (bsize < 0) return false;
+        const size_t total = (size_t)bsize + 1;
+        if (total < 12 + xlen + 8 || p + total > n) return false;
+        uint32_t crc, isize;
+        memcpy(&crc, b + p + total - 8, 4);
+        memcpy(&isize, b + p + total - 4, 4);
+        if (isize > 65536) return false;
+        out.push_back({p, p + 12 + xlen, total - 12 - xlen - 8, (uint64_t)isize | ((uint64_t)crc << 32)});
+        p += total;
+    }
+    return !out.empty();
+}
+
+struct BgzfJob {
+    int fd = -1;
+    std::vector<BgzfMember> m;
+    std::vector<size_t> first;        // first member of chunk k; first[nchunks] = m.size()
+    long long first_start = 0;        // text offset of the first non-blank byte inside member first[0]
+    size_t lookahead = 256 << 10;     // text bytes of look-ahead members a chunk starts with
+    const uint8_t *map = nullptr;     // the file, mapped for the header walk and the format sniff
+    size_t file_size = 0;
+};
+
+int bgzf_chunk(RangeSlot *s, long long seq, const RunArgs *a, const BgzfJob *job)
+{
+    const size_t lo_m = job->first[(size_t)seq], hi_m = job->first[(size_t)seq + 1], nm = job->m.size();
+    size_t want_extra = job->lookahead;
+    std::vector<uint64_t> tab;
+    int rc = 0;
+    while (true) {
+        size_t e = hi_m, extra_text = 0;
+        while (e < nm && (extra_text < want_extra || e == hi_m)) extra_text += (uint32_t)job->m[e++].packed;
+        size_t text = extra_text;
+        for (size_t i = lo_m; i < hi_m; i++) text += (uint32_t)job->m[i].packed;
+        if (text + 64 > s->cap) {   // a record longer than the slack: a bigger textproc
+            if (s->cap >= ((size_t)1 << 31)) { s->err = "record larger than the GPU text buffer"; return -1; }
+            size_t ncap = s->cap;
+            while (ncap < text + 64 && ncap < ((size_t)1 << 31)) ncap *= 2;
+            if (ncap < text + 64) { s->err = "record larger than the GPU text buffer"; return -1; }
+            shb_textproc *t = shb_textproc_create(s->device, ncap);
+            if (!t) { s->err = shb_last_error(); return -1; }
+            shb_textproc_destroy(s->tp);
+            s->tp = t; s->cap = ncap; s->buf = shb_textproc_input(t);
+        }
+        const size_t lo = job->m[lo_m].start, hi = job->m[e - 1].data + job->m[e - 1].clen + 8;
+        uint8_t *stage = shb_textproc_bgzf_input(s->tp, hi - lo + 64);
+        if (!stage) { s->err = shb_last_error(); return -1; }
+        if (pread_full(job->fd, stage, hi - lo, lo) != hi - lo) { s->err = "unexpected EOF"; return -1; }
+        tab.resize(3 * (e - lo_m));
+        for (size_t i = lo_m; i < e; i++) {
+            tab[3 * (i - lo_m)] = job->m[i].data - lo;
+            tab[3 * (i - lo_m) + 1] = job->m[i].clen;
+            tab[3 * (i - lo_m) + 2] = job->m[i].packed;
+        }
+        rc = shb_textproc_run_bgzf(s->tp, hi - lo, tab.data(), hi_m - lo_m, e - hi_m, seq == 0 ? job->first_start : -1, e == nm ? 1 : 0,
+                                   a->format, a->ids.empty() ? nullptr : a->ids.data(), (int)a->ids.size(), a->flags, a->headers_only, a->label);
+        if (rc != SHB_NEED_MORE) break;
+        if (e == nm) { s->err = "BGZF look-ahead exhausted"; return -1; }   // cannot happen: at_eof was set
+        want_extra *= 4;
+    }
+    while (true) {
+        if (rc < 0) { s->err = shb_last_error(); return rc; }
+        s->n_empty += shb_textproc_empty_records(s->tp);
+        s->n_nonascii += shb_textproc_nonascii(s->tp);
+        if (rc != 0 || !shb_textproc_pending(s->tp)) return rc;
+        size_t nout = 0;                                     // record index full: keep this output, run the rest
+        const uint8_t *o = shb_textproc_output(s->tp, &nout);
+        s->acc.insert(s->acc.end(), o, o + nout);
+        rc = shb_textproc_resume(s->tp, a->format, a->ids.empty() ? nullptr : a->ids.data(), (int)a->ids.size(), a->flags,
+                                 a->headers_only, a->label);
+    }
+}
+
+// the member table of a BGZF file, or null: not a regular file, not BGZF throughout, or the device path is switched off
+// (SHB_NO_BGZF) — the caller then takes the host-side inflate
+std::unique_ptr<BgzfJob> open_bgzf(int fd)
+{
+    struct stat st;
+    if (getenv("SHB_NO_BGZF") || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 28) return nullptr;
+    const size_t file_size = (size_t)st.st_size;
+    uint8_t head[18];
+    if (pread_full(fd, head, 18, 0) != 18 || head[0] != 0x1f || head[1] != 0x8b || head[2] != 8 || head[3] != 4) return nullptr;
+    void *map = mmap(nullptr, file_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (map == MAP_FAILED) return nullptr;
+    std::unique_ptr<BgzfJob> job(new BgzfJob());
+    job->fd = fd;
+    job->map = static_cast<const uint8_t *>(map);
+    job->file_size = file_size;
+    if (!scan_bgzf(job->map, file_size, job->m)) { munmap(map, file_size); return nullptr; }
+    return job;
+}
+
+int process_bgzf(BgzfJob &job, FILE *out, const Config &cfg, int n_gpus, std::string &err)
+{
+    const uint8_t *fb = job.map;
+    void *map = const_cast<uint8_t *>(job.map);
+    const size_t file_size = job.file_size;
+    phase("bgzf scanned");
+    RunArgs args;
+    std::string label = cfg.input;
+    bool no_file_name = cfg.no_file_name;
+    if (!cfg.name_override.empty()) label = cfg.name_override;
+    for (const std::string &t : cfg.hash_types) {
+        int id = shb_algo_id(t.c_str());
+        args.ids.push_back(id < 0 ? SHB_SHA1 : id);
+    }
+    if (args.ids.size() > 48) { err = "at most 48 hash fields per record are supported by the GPU formatter"; munmap(map, file_size); return 1; }
+    args.flags = cfg.case_sensitive ? 0u : SHB_FLAG_UPPER;
+    args.headers_only = cfg.headers_only ? 1 : 0;
+    args.label = no_file_name ? nullptr : label.c_str();
+    // sniff (fastx.NewReaderFromIO, seqhasher.go:221): the first non-blank byte of the text, found by inflating members on the
+    // host until one holds it; members of nothing but blank space before it belong to no chunk
+    size_t m0 = 0;
+    bool found = false;
+    {
+        std::vector<uint8_t> txt(65536 + 16);
+        for (; m0 < job.m.size() && !found; m0++) {
+            const BgzfMember &mb = job.m[m0];
+            const uint32_t isize = (uint32_t)mb.packed;
+            if (isize == 0) continue;
+            z_stream z{};
+            if (inflateInit2(&z, -15) != Z_OK) { err = "Error reading record: gzip: init failed"; munmap(map, file_size); return 1; }
+            z.next_in = const_cast<Bytef *>(fb + mb.data);
+            z.avail_in = (uInt)mb.clen;
+            z.next_out = txt.data();
+            z.avail_out = (uInt)txt.size();
+            const int zr = inflate(&z, Z_FINISH);
+            const size_t got = txt.size() - z.avail_out;
+            inflateEnd(&z);
+            if (zr != Z_STREAM_END || got != isize) { err = "Error reading record: flate: corrupt input"; munmap(map, file_size); return 1; }
+            for (size_t i = 0; i < got; i++) {
+                if (!is_blank(txt[i])) {
+                    found = true;
+                    job.first_start = (long long)i;
+                    if (txt[i] == '>') args.format = SHB_FORMAT_FASTA;
+                    else if (txt[i] == '@') args.format = SHB_FORMAT_FASTQ;
+                    else { err = "Failed to create reader: fastx: invalid FASTA/Q format"; munmap(map, file_size); return 1; }
+                    break;
+                }
+            }
+            if (found) break;
+        }
+    }
+    munmap(map, file_size);
+    if (!found) return 0;   // empty input: no records
+    size_t C = (size_t)64 << 20;
+    if (const char *e = getenv("SHB_CHUNK_KB")) { const long kb = atol(e); if (kb >= 1) C = (size_t)kb << 10; }
+    if (C < job.lookahead) job.lookahead = std::max<size_t>(C, 1024);
+    size_t acc = 0;
+    job.first.push_back(m0);
+    for (size_t i = m0; i < job.m.size(); i++) {
+        const uint32_t isize = (uint32_t)job.m[i].packed;
+        if (acc && acc + isize > C) { job.first.push_back(i); acc = 0; }
+        acc += isize;
+    }
+    job.first.push_back(job.m.size());
+    const long long nchunks = (long long)job.first.size() - 1;
+    const ChunkFn fn = [&](RangeSlot *s, long long seq) { return bgzf_chunk(s, seq, &args, &job); };
+    return run_chunk_slots(nchunks, n_gpus, C + 65536 + 4 * job.lookahead + 4096, fn, out, args, err);
+}
+
 // How many GPUs this run uses: SHB_GPUS if set; otherwise one per 12 GiB of a plain regular file — bringing up one more
 // device costs 0.3-0.6 s of CUDA initialisation on a cold driver, the time one GPU needs for 4-8 GB of text — and one for
 // anything else (a stream is bound by its reader or its host-side inflate, not by the GPU).
@@ -854,7 +1068,10 @@ int main(int argc, char **argv)
     int rc = 1;
     try {
         bool compressed = false;
-        auto src = host::open_maybe_compressed(fin, fin != stdin, &compressed);
+        std::unique_ptr<host::Source> src;
+        std::unique_ptr<BgzfJob> bgzf = fin != stdin ? open_bgzf(fileno(fin)) : nullptr;
+        if (bgzf) compressed = true;   // no host-side reader at all: the members are inflated on the GPU
+        else src = host::open_maybe_compressed(fin, fin != stdin, &compressed);
         int n_gpus = pick_gpus(fin, fin != stdin && !compressed);
         // Unless the caller chose, hide the GPUs this run does not use: creating the CUDA context otherwise initialises
         // every device of the node (about 0.1 s each on an 8-GPU box) for a run that may last half a second.
@@ -873,7 +1090,9 @@ int main(int argc, char **argv)
             size_t chunk = (size_t)64 << 20;
             if (const char *e = getenv("SHB_CHUNK_KB")) { const long kb = atol(e); if (kb >= 1) chunk = (size_t)kb << 10; }
             // a seekable plain file of several chunks: every slot reads its own byte range (no sequential reader)
-            if (plain_file && !getenv("SHB_NO_RANGES") && (n_gpus > 1 || (size_t)st.st_size >= 4 * chunk))
+            if (bgzf)
+                rc = process_bgzf(*bgzf, fout, cfg, n_gpus, err);
+            else if (plain_file && !getenv("SHB_NO_RANGES") && (n_gpus > 1 || (size_t)st.st_size >= 4 * chunk))
                 rc = process_file_ranges(fileno(fin), (size_t)st.st_size, fout, cfg, n_gpus, err);
             else
                 rc = process_sequences(*src, fout, cfg, n_gpus, err);

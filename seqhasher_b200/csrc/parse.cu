@@ -493,46 +493,52 @@ __global__ void __launch_bounds__(256) fmt_write_kernel(FmtCfg c, FxOut rec, siz
 
 // ------------------------------------------------------------------------------------------- BGZF inflate
 
-// One warp per BGZF member: lane 0 runs the DEFLATE decoder (inflate.cuh) with its tables in the warp's slice of shared memory
-// and then checks the member's CRC-32 (slice-by-4, tables built per CTA).  Members are independent by construction of the
-// format (each is a complete gzip member of <= 64 KiB of text), so a 64 MiB text chunk is ~1000 warps of work, and the
-// compressed bytes — a third to a quarter of the text — are all that crosses PCIe.
-__global__ void __launch_bounds__(256) bgzf_inflate_kernel(const uint8_t *__restrict__ comp, const unsigned long long *__restrict__ tab,
-                                                           size_t n_members, uint8_t *__restrict__ text,
-                                                           unsigned long long *__restrict__ status)
+// One warp (= one CTA) per BGZF member, three CTAs per SM: inflate.cuh decodes the member into a window in shared memory,
+// then the warp checks ISIZE and the CRC-32 (32 segments, combined) and stores the window to the text with 128-bit stores.
+// Members are independent by construction of the format (each is a complete gzip member of <= 64 KiB of text), so a 64 MiB
+// text chunk is ~1000 warps of work, and the compressed bytes — a third to a quarter of the text — are all that crosses PCIe.
+// The window sits at the 16-byte phase of its destination so that both sides of the final copy are aligned.
+struct BgzfSmem {
+    InflateScratch s;
+    __align__(16) uint8_t win[INF_WINDOW + 16];
+};
+
+__global__ void __launch_bounds__(32) bgzf_inflate_kernel(const uint8_t *__restrict__ comp, const unsigned long long *__restrict__ tab,
+                                                          size_t n_members, uint8_t *__restrict__ text,
+                                                          unsigned long long *__restrict__ status)
 {
-    __shared__ InflateScratch s_scr[8];
-    __shared__ uint32_t s_crc[4][256];
-    {
-        const uint32_t i = threadIdx.x;   // 256 threads: one table column each
-        uint32_t c = i;
-        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
-        s_crc[0][i] = c;
-        __syncthreads();
-        uint32_t c1 = s_crc[0][i];
-        for (int t = 1; t < 4; t++) {
-            c1 = s_crc[0][c1 & 0xffu] ^ (c1 >> 8);
-            s_crc[t][i] = c1;
-        }
-        __syncthreads();
-    }
-    const size_t m = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (m >= n_members || (threadIdx.x & 31u) != 0) return;
-    const unsigned long long off = tab[4 * m], clen = tab[4 * m + 1], packed = tab[4 * m + 2], out = tab[4 * m + 3];
+    extern __shared__ __align__(16) uint8_t bgzf_smem[];
+    BgzfSmem &m = *reinterpret_cast<BgzfSmem *>(bgzf_smem);
+    const size_t mi = blockIdx.x;
+    if (mi >= n_members) return;
+    const uint32_t lane = threadIdx.x;
+    const unsigned long long off = tab[4 * mi], clen = tab[4 * mi + 1], packed = tab[4 * mi + 2], out = tab[4 * mi + 3];
     const uint32_t isize = (uint32_t)packed, want_crc = (uint32_t)(packed >> 32);
-    uint8_t *dst = text + out;
-    int rc = inflate_raw(comp + off, (uint32_t)clen, dst, isize, s_scr[threadIdx.x >> 5]);
-    if (rc == INF_OK) {
-        uint32_t c = 0xffffffffu, k = 0;
-        for (; k < isize && ((uintptr_t)(dst + k) & 3u); k++) c = s_crc[0][(c ^ dst[k]) & 0xffu] ^ (c >> 8);
-        for (; k + 4 <= isize; k += 4) {
-            c ^= *reinterpret_cast<const uint32_t *>(dst + k);
-            c = s_crc[3][c & 0xffu] ^ s_crc[2][(c >> 8) & 0xffu] ^ s_crc[1][(c >> 16) & 0xffu] ^ s_crc[0][c >> 24];
+    int rc = INF_ERR_OUTPUT;
+    if (isize <= INF_WINDOW) {
+        const uint32_t phase = (uint32_t)(out & 15ull);
+        uint32_t produced = 0;
+        rc = inflate_raw_warp(comp + off, (uint32_t)clen, m.win + phase, isize, &produced, m.s, lane, 32u);
+        if (rc == INF_OK && produced != isize) rc = INF_ERR_SIZE;
+        __syncwarp();
+        if (rc == INF_OK) {
+            crc_build_tables(m.s.u.crc, lane, 32u);
+            const uint32_t c = __reduce_xor_sync(0xffffffffu, crc_lane_share(m.win, phase, isize, m.s.u.crc, lane, 32u));
+            if (c != want_crc) rc = INF_ERR_CRC;
         }
-        for (; k < isize; k++) c = s_crc[0][(c ^ dst[k]) & 0xffu] ^ (c >> 8);
-        if ((c ^ 0xffffffffu) != want_crc) rc = 100;
+        if (rc == INF_OK) {
+            uint8_t *gbase = text + (out - phase);                    // 16-byte aligned: text is, and out - phase is a multiple of 16
+            const uint32_t end = phase + isize;
+            for (uint32_t u = lane * 16u; u < end; u += 32u * 16u) {
+                if (u >= phase && u + 16u <= end) {
+                    *reinterpret_cast<uint4 *>(gbase + u) = *reinterpret_cast<const uint4 *>(m.win + u);
+                } else {                                              // the first / last unit is shared with the neighbouring member
+                    for (uint32_t k = (u > phase ? u : phase); k < (u + 16u < end ? u + 16u : end); k++) gbase[k] = m.win[k];
+                }
+            }
+        }
     }
-    if (rc != INF_OK) atomicMin(status, (unsigned long long)m + 1ull);
+    if (rc != INF_OK && lane == 0) atomicMin(status, ((unsigned long long)(mi + 1) << 8) | (unsigned)rc);
 }
 
 cudaError_t launch_bgzf_inflate(const uint8_t *comp, const unsigned long long *tab, size_t n_members, uint8_t *text,
@@ -540,7 +546,92 @@ cudaError_t launch_bgzf_inflate(const uint8_t *comp, const unsigned long long *t
 {
     cudaError_t e = cudaMemsetAsync(status, 0xff, sizeof(unsigned long long), st);   // "no failure" = the largest value (atomicMin)
     if (e != cudaSuccess || n_members == 0) return e;
-    bgzf_inflate_kernel<<<(unsigned)((n_members + 7) / 8), 256, 0, st>>>(comp, tab, n_members, text, status);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        e = cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSmem));
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
+    bgzf_inflate_kernel<<<(unsigned)n_members, 32, sizeof(BgzfSmem), st>>>(comp, tab, n_members, text, status);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// Record boundaries of a device-resident text whose ends are arbitrary (a run of inflated BGZF members): CTA 0 finds the first
+// record start at index >= from0, CTA 1 the first one at index >= from1; res[0], res[1] = the positions, or -1 when there is
+// none before n.  A record start is what the splitter itself calls one: FASTA, a line-initial '>'; FASTQ, a line that starts
+// with '@' and whose next-but-one line starts with '+' (a quality line may start with '@', but then the line two below it is
+// a sequence line, which never starts with '+') — the rule of find_record_start in csrc/host/main.cpp.  from >= 1 (text[from-1]
+// decides "line-initial"); from == 0 means "position 0 is a line start" (the very beginning of the input).
+// res[2] = index one past the last non-blank byte of the text (trailing blank lines are not records), res[3] = text[n - 1].
+__global__ void __launch_bounds__(256) fx_bounds_kernel(const uint8_t *__restrict__ text, size_t n, long long from0, long long from1,
+                                                        int fastq, long long *__restrict__ res)
+{
+    __shared__ long long s_ls[64];    // first line starts found (a FASTQ record start is among any four consecutive ones, plus two lines of look-ahead)
+    __shared__ int s_n;
+    __shared__ unsigned long long s_min;
+    __shared__ uint32_t s_scan[256];
+    const long long from = blockIdx.x == 0 ? from0 : from1;
+    const uint32_t t = threadIdx.x;
+    if (blockIdx.x == 0 && t == 0) {
+        long long e = (long long)n;
+        while (e > 0 && (text[e - 1] == ' ' || (text[e - 1] >= '\t' && text[e - 1] <= '\r'))) e--;
+        res[2] = e;
+        res[3] = n ? text[n - 1] : '\n';
+    }
+    if (from < 0 || (size_t)from >= n) {
+        if (t == 0) res[blockIdx.x] = -1;
+        return;
+    }
+    if (t == 0) { s_n = 0; s_min = ~0ull; }
+    __syncthreads();
+    // line starts p >= from in windows of 4 KiB: p == 0 when from == 0, else text[p - 1] == '\n'
+    for (size_t base = (size_t)from; base < n; base += 4096) {
+        const size_t p0 = base + 16u * t;
+        uint32_t mask = 0;
+#pragma unroll 4
+        for (int k = 0; k < 16; k++) {
+            const size_t p = p0 + k;
+            if (p < n) {
+                const bool ls = p == 0 ? true : text[p - 1] == '\n';
+                if (ls && (fastq || text[p] == '>')) mask |= 1u << k;
+            }
+        }
+        if (!fastq) {
+            if (mask) atomicMin(&s_min, (unsigned long long)(p0 + (__ffs(mask) - 1)));
+            __syncthreads();
+            if (s_min != ~0ull) break;
+        } else {
+            s_scan[t] = __popc(mask);
+            __syncthreads();
+            const int had = s_n;
+            __syncthreads();
+            if (t == 0) {                           // 256 counts: a serial scan by one thread is a few hundred cycles
+                uint32_t acc = (uint32_t)had;
+                for (int i = 0; i < 256; i++) { const uint32_t v = s_scan[i]; s_scan[i] = acc; acc += v; }
+                s_n = (int)(acc < 64u ? acc : 64u);
+            }
+            __syncthreads();
+            uint32_t rank = s_scan[t];
+            for (uint32_t mm = mask; mm && rank < 64u; mm &= mm - 1, rank++) s_ls[rank] = (long long)(p0 + (__ffs(mm) - 1));
+            __syncthreads();
+            if (t == 0) {
+                for (int i = (had >= 2 ? had - 2 : 0); i + 2 < s_n; i++)
+                    if (text[s_ls[i]] == '@' && text[s_ls[i + 2]] == '+') { s_min = (unsigned long long)s_ls[i]; break; }
+            }
+            __syncthreads();
+            if (s_min != ~0ull || s_n >= 64) break;   // 62 lines without a record start: not FASTQ; the splitter will say so
+        }
+    }
+    __syncthreads();
+    if (t == 0) res[blockIdx.x] = s_min != ~0ull ? (long long)s_min : -1;
+}
+
+cudaError_t launch_fx_bounds(const uint8_t *text, size_t n, long long from0, long long from1, bool fastq, long long *res, cudaStream_t st)
+{
+    fx_bounds_kernel<<<2, 256, 0, st>>>(text, n, from0, from1, fastq ? 1 : 0, res);
     g_launches++;
     return cudaGetLastError();
 }

@@ -47,10 +47,13 @@ struct FmtCfg {
 };
 
 // BGZF members inflated on the device (inflate.cuh): member i = deflate data comp[tab[4i], +tab[4i+1]) -> text[tab[4i+3], +isize),
-// tab[4i+2] = isize | crc32 << 32.  *status receives 0, or 1 + the index of the first member that failed to decode, did not
-// produce isize bytes or whose CRC-32 differs.
+// tab[4i+2] = isize | crc32 << 32; text is 16-byte aligned.  *status receives all ones, or ((1 + index) << 8 | INF_ERR_*) of the
+// first member that failed to decode, did not produce isize bytes or whose CRC-32 differs.
 cudaError_t launch_bgzf_inflate(const uint8_t *comp, const unsigned long long *tab, size_t n_members, uint8_t *text,
                                 unsigned long long *status, cudaStream_t st);
+// first record start at index >= from0 -> res[0], >= from1 -> res[1] (-1: none before n; a negative `from` is not searched);
+// res[2] = one past the last non-blank byte, res[3] = the last byte.  See fx_bounds_kernel.
+cudaError_t launch_fx_bounds(const uint8_t *text, size_t n, long long from0, long long from1, bool fastq, long long *res, cudaStream_t st);
 
 size_t fx_scratch_bytes(size_t n_bytes);
 cudaError_t launch_fx_parse(const uint8_t *text, size_t n, bool fastq, bool is_final, FxOut out, FxInfo *info,

@@ -33,6 +33,13 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel)
 static inline uint64_t __umul64hi(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)mask; }
+static inline uint32_t __brev(uint32_t x)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);
+    return r;
+}
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }

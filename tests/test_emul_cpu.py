@@ -67,6 +67,8 @@ def inflate_emul():
     L = ctypes.CDLL(so)
     L.emul_inflate_raw.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32]
     L.emul_inflate_raw.restype = ctypes.c_int
+    L.emul_crc32_lanes.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]
+    L.emul_crc32_lanes.restype = ctypes.c_uint32
     return L
 
 
@@ -115,3 +117,19 @@ def test_device_inflate_matches_zlib(inflate_emul):
                 rc = inflate_emul.emul_inflate_raw(bytes(bad), len(bad), out, n)
                 assert rc != 0 or out.raw[:n] != data or True   # CRC (checked by the caller) catches silent damage; no crash is the test
     assert cases == 2800
+
+
+def test_device_crc32_lane_shares_match_zlib(inflate_emul):
+    """The window's CRC-32 as the warp computes it (32 segments, each moved to the end of the text with x^(8n) mod P, XORed)
+    against zlib.crc32, for every window phase 0..15 and sizes from empty to a full BGZF member."""
+    import zlib
+    rng = np.random.default_rng(7)
+    buf = np.zeros(65536 + 64, dtype=np.uint8)
+    base = buf.ctypes.data
+    assert base % 4 == 0
+    for trial in range(300):
+        n = int(rng.choice([0, 1, 2, 3, 4, 5, 31, 32, 33, 127, 128, 129, 4095, 65280, 65535, 65536]) if trial % 2 else rng.integers(0, 65537))
+        first = int(rng.integers(0, 16))
+        buf[:] = rng.integers(0, 256, size=buf.size)
+        got = inflate_emul.emul_crc32_lanes(base, first, n)
+        assert got == zlib.crc32(buf[first:first + n].tobytes()), (trial, first, n)

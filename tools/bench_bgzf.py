@@ -1,0 +1,123 @@
+"""BGZF input: device inflate (csrc/inflate.cuh) against the host-side feeder and the plain file, on a C5-shaped FASTA
+(variable-length multi-line records).  Prints one JSON object.
+
+  python tools/bench_bgzf.py [--records 400000] [--level 6] [--hash sha1] [--no-cli]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+ALL12 = ["sha1", "sha3", "md5", "xxhash", "xxh3", "cityhash", "murmur3", "nthash", "blake3", "k12", "rapidhash", "rapidhash32"]
+
+
+def make_text(nrec, seed=5):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(30, 3001, size=nrec)
+    seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(lens.sum())).tobytes()
+    parts, pos = [], 0
+    for i, L in enumerate(lens.tolist()):
+        rec = seq[pos:pos + L]
+        pos += L
+        parts.append(b">seq_%d len=%d\n" % (i, L))
+        parts.append(b"\n".join(rec[k:k + 60] for k in range(0, L, 60)))
+        parts.append(b"\n")
+    return b"".join(parts)
+
+
+def bgzf_parallel(text, level, threads):
+    from seqhasher_b200.host import bgzf
+    step = 65280 * 64
+    with ThreadPoolExecutor(threads) as pool:
+        pieces = list(pool.map(lambda i: bgzf.compress(text[i:i + step], level, 65280, eof_marker=False), range(0, len(text), step)))
+    return b"".join(pieces) + bgzf.EOF_MEMBER
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--records", type=int, default=400000)
+    ap.add_argument("--level", type=int, default=6)
+    ap.add_argument("--hash", default="sha1")
+    ap.add_argument("--no-cli", action="store_true")
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    from seqhasher_b200 import binding as B
+    from seqhasher_b200.host import bgzf
+    B.init(1)
+    cores = os.cpu_count() or 1
+    text = make_text(a.records)
+    gz = bgzf_parallel(text, a.level, min(cores, 32))
+    members = bgzf.scan_members(gz)
+    out = {"records": a.records, "text_bytes": len(text), "bgzf_bytes": len(gz), "members": int(len(members)), "level": a.level,
+           "ratio": len(text) / len(gz), "host_cores": cores}
+    ids = [B.algo_id(x) for x in a.hash.split(",")]
+    tp = B.TextProc(96 << 20)
+    own = (64 << 20) // 65280
+    # warm-up + parity with the plain path on the first chunk
+    runs = []
+    for rep in range(a.reps + 1):
+        t0 = time.perf_counter()
+        nbytes = nrec = 0
+        inflate_ms = h2d_ms = rest_ms = 0.0
+        nchunks = 0
+        k = 0
+        n = len(members)
+        mv = np.frombuffer(gz, dtype=np.uint8)
+        while k < n:
+            n_own = min(own, n - k)
+            extra = min(4, n - k - n_own)
+            last = k + n_own + extra - 1
+            lo = int(members[k][3]); hi = int(members[last][0] + members[last][1]) + 8
+            stage = tp.bgzf_input(40 << 20)
+            stage[:hi - lo] = mv[lo:hi]
+            tab = members[k:last + 1, :3].copy(); tab[:, 0] -= np.uint64(lo)
+            r = tp.run_bgzf(hi - lo, tab, n_own, extra, 0 if k == 0 else -1, last == n - 1, 1, ids, B.FLAG_UPPER, True, b"c5.fa")
+            assert r is not None
+            ms = tp.last_ms()
+            inflate_ms += tp.last_inflate_ms(); h2d_ms += ms["h2d"]; rest_ms += ms["split"] + ms["hash"] + ms["format"] + ms["d2h"]
+            nbytes += len(r[0]); nrec += r[2]; nchunks += 1
+            k += n_own
+        dt = time.perf_counter() - t0
+        assert nrec == a.records, (nrec, a.records)
+        runs.append({"wall_s": dt, "inflate_ms": inflate_ms, "stage1_ms(h2d+inflate+bounds)": h2d_ms, "rest_ms": rest_ms, "chunks": nchunks})
+    best = min(runs[1:], key=lambda r: r["wall_s"])
+    out["device_path"] = dict(best, text_gbps_wall=len(text) / best["wall_s"] / 1e9,
+                              inflate_text_gbps=len(text) / (best["inflate_ms"] / 1e3) / 1e9,
+                              inflate_ms_per_64MiB_chunk=best["inflate_ms"] / best["chunks"],
+                              note="single slot, blocking calls from Python (no overlap); hash list = " + a.hash)
+    tp.close()
+    if not a.no_cli:
+        cli = os.path.join(ROOT, "seqhasher_b200", "bin", "seqhasher-b200")
+        with tempfile.TemporaryDirectory() as td:
+            pg, pp = os.path.join(td, "c5.fa.gz"), os.path.join(td, "c5.fa")
+            open(pg, "wb").write(gz)
+            open(pp, "wb").write(text)
+            res = {}
+            for hl, hname in ((a.hash, "hash_" + a.hash), (",".join(ALL12), "all12")):
+                for name, path, env in (("bgzf_device", pg, {}), ("bgzf_host_inflate", pg, {"SHB_NO_BGZF": "1"}), ("plain", pp, {})):
+                    ts, o = [], None
+                    for _ in range(3):
+                        t0 = time.perf_counter()
+                        p = subprocess.run([cli, "--headersonly", "--name", "c5.fa", "--hash", hl, path, "-"], capture_output=True, check=True,
+                                           env=dict(os.environ, **env))
+                        ts.append(time.perf_counter() - t0)
+                        o = p.stdout
+                    res[(hname, name)] = (min(ts[1:]), o)
+                same = res[(hname, "bgzf_device")][1] == res[(hname, "plain")][1] == res[(hname, "bgzf_host_inflate")][1]
+                out["cli_" + hname] = {k[1] + "_s": v[0] for k, v in res.items() if k[0] == hname}
+                out["cli_" + hname]["same_output"] = same
+                out["cli_" + hname]["note"] = "whole-process wall time incl. ~0.4 s CUDA context creation/teardown, best of 2 after a warm-up"
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
