@@ -12,12 +12,15 @@
 // identical replicas: same registers, same shared-memory reads (broadcasts), and only idempotent same-value stores.  That costs
 // nothing (a warp instruction takes one issue slot whatever the lane count) and it leaves every lane with the decoder state,
 // so the parts that ARE parallel need no hand-over:
-//   * a match (length, distance) is copied by the lanes side by side, 32 bytes per step, in the member's output window, which
-//     lives in shared memory (a BGZF member is <= 64 KiB of text; shared-memory latency instead of an L2 round trip per copy);
+//   * a match (length, distance) is copied by the lanes side by side, 32 bytes per step, straight in the text buffer (global
+//     memory; a BGZF member never reaches behind its own first byte).  The store of a copy is held back until the next match is
+//     decoded, so the load's L2 round trip overlaps ~60 instructions of Huffman decoding instead of stalling the warp;
 //   * the literal/length table holds up to three literals per 10-bit look-up (DNA text: A/C/G/T get 2-3-bit codes), written by
 //     lanes 0..2 at once; the table is built lane-parallel from the per-code table;
-//   * the finished window is stored to global memory with 128-bit stores and its CRC-32 is computed by 32 lanes on 32
-//     segments, combined with the x^(8n) mod P operator (the crc32_combine identity).
+//   * the CRC-32 of the finished text is computed by 32 lanes on 32 segments, combined with the x^(8n) mod P operator (the
+//     crc32_combine identity).
+// Only the tables live in shared memory (10 KiB per warp), so ~20 members are resident per SM and the schedulers interleave
+// their dependent chains (a first version kept the 64 KiB window in shared memory: 3 warps per SM, 12 % issue utilisation).
 // Lanes are replicas, not lock-stepped by assumption: every cross-lane dependency sits behind a __syncwarp().
 //
 // Written as plain C++ (lane, nl = lane index and lane count) so that tests/emul compiles it for the host with nl = 1 and
@@ -44,18 +47,26 @@ enum : int {
 constexpr int INF_MAXBITS = 15, INF_MAXLCODES = 286, INF_MAXDCODES = 30, INF_FIXLCODES = 288;
 constexpr int INF_LBITS = 10, INF_DBITS = 8, INF_CBITS = 7;
 constexpr uint32_t INF_WINDOW = 65536;   // most text one BGZF member holds
+#ifdef __CUDA_ARCH__
+#define INF_OPAQUE(p) asm volatile("" : "+l"(p))        // keep the pointer in registers instead of re-deriving it from the kernel arguments
+#else
+#define INF_OPAQUE(p) (void)(p)
+#endif
 constexpr uint32_t INF_COPY_LANES = 32;  // lanes that copy a match side by side (the warp; the host emulation keeps the same case split)
 
-// kinds of a literal/length table entry: bits 0-3 = bits to drop, bits 4-6 = kind, bits 8-31 = payload
-// kind 1..3: that many literals (payload bytes in output order); kind 4: payload = symbol - 256 (0 = end of block,
-// 1..29 = length symbol); kind 0: code longer than INF_LBITS bits, take the bit-by-bit path
+// literal/length table entry: bits 0-3 = code bits to drop, bits 4-6 = kind, bits 8-31 = payload
+//   kind 1..3: that many literals (payload bytes in output order)
+//   kind 4: a length symbol: bits 8-16 = base length, bits 17-19 = number of extra bits
+//   kind 5: end of block;  kind 6: a symbol that does not exist (286, 287)
+//   kind 0: code longer than INF_LBITS bits, take the bit-by-bit path
+// distance table entry: bits 0-3 = code bits, bits 4-7 = number of extra bits, bits 8-23 = base distance; 0 = bit-by-bit path
 struct InflateScratch {
     uint32_t multi[1 << INF_LBITS];
     union {
-        uint16_t single[1 << INF_LBITS];   // (symbol << 4) | code length; only while `multi` is being built
+        uint16_t single[1 << INF_LBITS];   // (symbol << 4) | code length; while `multi` is built, and for the code-length code of a header
         uint32_t crc[4][256];              // slice-by-4 tables; only after the last block
     } u;
-    uint16_t fastd[1 << INF_DBITS];        // (distance symbol << 4) | code length; also serves the code-length code of a header
+    uint32_t fastd[1 << INF_DBITS];
     uint16_t lcount[INF_MAXBITS + 1], lsym[INF_FIXLCODES], dcount[INF_MAXBITS + 1], dsym[INF_MAXDCODES + 2];
     uint8_t lengths[INF_MAXLCODES + INF_MAXDCODES + 4];
 };
@@ -79,12 +90,12 @@ static __constant__ uint32_t k_crc_x2n[32] = {
 
 // ---- bit reader: aligned 32-bit words of the compressed stream, one word fetched ahead of its use ----
 struct InfBits {
-    const uint32_t *w;       // 4-byte-aligned base at or before the first byte of the stream
+    const uint32_t *w;       // 4-byte-aligned base at or before the first byte read
     uint32_t widx, nwords;   // index of `next`; words that hold stream bytes
     uint32_t next;           // w[widx], already loaded
     uint64_t buf;
     int cnt;                 // valid bits in buf
-    uint32_t merged_bits;    // stream bits that have entered buf
+    uint32_t base_bits;      // stream position of bit 0 of w[0], plus 2^31 (it may lie up to 24 bits before the stream)
     uint32_t limit_bits;     // 8 * stream length
 };
 
@@ -102,7 +113,7 @@ __device__ __forceinline__ void inf_init(InfBits &b, const uint8_t *src, uint32_
     b.cnt = 32 - 8 * (int)skip;
     b.widx = 1;
     b.next = inf_word(b, 1);
-    b.merged_bits = 8u * at + (uint32_t)b.cnt;
+    b.base_bits = 0x80000000u + 8u * at - 8u * skip;
     b.limit_bits = 8u * src_len;
 }
 // at least 32 valid bits afterwards (past the end of the stream: zeros, and inf_overrun() turns true once they are consumed)
@@ -111,7 +122,6 @@ __device__ __forceinline__ void inf_refill(InfBits &b)
     if (b.cnt <= 32) {
         b.buf |= (uint64_t)b.next << b.cnt;
         b.cnt += 32;
-        b.merged_bits += 32u;
         b.widx++;
         b.next = inf_word(b, b.widx);
     }
@@ -124,7 +134,8 @@ __device__ __forceinline__ uint32_t inf_take(InfBits &b, int n)   // n <= 16, af
     inf_drop(b, n);
     return v;
 }
-__device__ __forceinline__ uint32_t inf_used_bits(const InfBits &b) { return b.merged_bits - (uint32_t)b.cnt; }
+// stream bits consumed so far (bits in buf are not consumed yet)
+__device__ __forceinline__ uint32_t inf_used_bits(const InfBits &b) { return b.base_bits + 32u * b.widx - (uint32_t)b.cnt - 0x80000000u; }
 __device__ __forceinline__ bool inf_overrun(const InfBits &b) { return inf_used_bits(b) > b.limit_bits; }
 
 // canonical Huffman code from code lengths: count[len], symbol[] sorted by (length, symbol).
@@ -193,6 +204,29 @@ __device__ __forceinline__ void inf_build_direct(const uint16_t *count, const ui
     __syncwarp();
 }
 
+// distance look-up: base and extra-bit count baked into the entry
+__device__ __forceinline__ void inf_build_dist(const uint16_t *count, const uint16_t *symbol, uint32_t *tab, uint32_t lane, uint32_t nl)
+{
+    const uint32_t size = 1u << INF_DBITS;
+    for (uint32_t i = lane; i < size; i += nl) tab[i] = 0;
+    __syncwarp();
+    uint32_t code = 0, index = 0;
+    for (int len = 1; len <= INF_DBITS; len++) {
+        const uint32_t c = count[len];
+        for (uint32_t k = 0; k < c; k++) {
+            const uint32_t sym = symbol[index + k];
+            const uint32_t di = k_inf_dist[sym & 31u];
+            const uint32_t r = __brev(code + k) >> (32 - len);
+            // a symbol that does not exist (30, 31) keeps entry 0: the bit-by-bit path reports it
+            const uint32_t e = di ? ((uint32_t)len | ((di >> 16) << 4) | ((di & 0xffffu) << 8)) : 0u;
+            for (uint32_t fill = r + (lane << len); fill < size; fill += nl << len) tab[fill] = e;
+        }
+        index += c;
+        code = (code + c) << 1;
+    }
+    __syncwarp();
+}
+
 // literal/length look-up with up to three literals per entry, from the per-code table u.single
 __device__ __forceinline__ void inf_build_multi(InflateScratch &s, uint32_t lane, uint32_t nl)
 {
@@ -202,8 +236,11 @@ __device__ __forceinline__ void inf_build_multi(InflateScratch &s, uint32_t lane
         uint32_t out = 0;
         if (e1) {
             const uint32_t l1 = e1 & 15u, s1 = e1 >> 4;
-            if (s1 >= 256u) {
-                out = l1 | (4u << 4) | ((s1 - 256u) << 8);
+            if (s1 == 256u) {
+                out = l1 | (5u << 4);
+            } else if (s1 > 256u) {
+                const uint32_t li = k_inf_len[(s1 - 256u) & 31u];
+                out = li ? (l1 | (4u << 4) | ((li & 0xffffu) << 8) | ((li >> 16) << 17)) : (l1 | (6u << 4));
             } else {
                 uint32_t n = 1, total = l1, lits = s1 << 8, rem = i >> l1, avail = INF_LBITS - l1;
                 const uint32_t e2 = s.u.single[rem];
@@ -223,53 +260,72 @@ __device__ __forceinline__ void inf_build_multi(InflateScratch &s, uint32_t lane
     __syncwarp();
 }
 
-// the symbols of one block, tables in s; out[0, cap) is the member's window
+// the symbols of one block, tables in s; out[0, cap) is the member's text
 __device__ __forceinline__ int inf_codes(InfBits &b, InflateScratch &s, uint8_t *out, uint32_t &pos, uint32_t cap, uint32_t lane, uint32_t nl)
 {
-    while (true) {
+    // the held-back store of the last short copy (this lane's byte)
+    uint8_t *pend_at = nullptr;
+    uint32_t pend_val = 0;
+    int rc = -1;
+    uint8_t *lane0 = out + lane;                        // this lane's column of the text: one 64-bit add per access
+    INF_OPAQUE(lane0);
+    while (rc < 0) {
         inf_refill(b);
         const uint32_t e = s.multi[inf_peek(b, INF_LBITS)];
         const uint32_t kind = (e >> 4) & 7u;
-        uint32_t sym;   // symbol - 256
-        if (kind - 1u < 3u) {
-            if (pos + kind > cap) return INF_ERR_OUTPUT;
-            for (uint32_t l = lane; l < kind; l += nl) out[pos + l] = (uint8_t)(e >> (8u + 8u * l));
+        uint32_t len, extra;
+        if (kind == 4u) {                               // a length symbol: the usual case in text that compresses
+            inf_drop(b, (int)(e & 15u));
+            len = (e >> 8) & 0x1ffu;
+            extra = (e >> 17) & 7u;
+        } else if (kind - 1u < 3u) {
+            if (pos + kind > cap) { rc = INF_ERR_OUTPUT; break; }
+            for (uint32_t l = lane; l < kind; l += nl) lane0[pos + l - lane] = (uint8_t)(e >> (8u + 8u * l));
             pos += kind;
             inf_drop(b, (int)(e & 15u));
             continue;
-        } else if (kind == 4u) {
+        } else if (kind == 5u) {
             inf_drop(b, (int)(e & 15u));
-            sym = (e >> 8) & 0xffu;
+            rc = inf_overrun(b) ? INF_ERR_INPUT : INF_OK;
+            break;
+        } else if (kind == 6u) {
+            rc = INF_ERR_SYMBOL;
+            break;
         } else {
             const int v = inf_decode_slow(b, s.lcount, s.lsym);
-            if (v < 0) return INF_ERR_SYMBOL;
+            if (v < 0) { rc = INF_ERR_SYMBOL; break; }
             if (v < 256) {
-                if (pos >= cap) return INF_ERR_OUTPUT;
+                if (pos >= cap) { rc = INF_ERR_OUTPUT; break; }
                 if (lane == 0) out[pos] = (uint8_t)v;
                 pos++;
                 continue;
             }
-            sym = (uint32_t)v - 256u;
+            if (v == 256) { rc = inf_overrun(b) ? INF_ERR_INPUT : INF_OK; break; }
+            const uint32_t li = k_inf_len[(uint32_t)(v - 256) & 31u];
+            if (li == 0) { rc = INF_ERR_SYMBOL; break; }
+            len = li & 0xffffu;
+            extra = li >> 16;
         }
-        if (sym == 0) return inf_overrun(b) ? INF_ERR_INPUT : INF_OK;
-        const uint32_t li = k_inf_len[sym & 31u];
-        if (li == 0) return INF_ERR_SYMBOL;
-        const uint32_t len = (li & 0xffffu) + inf_take(b, (int)(li >> 16));
+        len += inf_take(b, (int)extra);
         inf_refill(b);
-        int ds;
-        const uint32_t de = s.fastd[inf_peek(b, INF_DBITS)];
-        if (de) { inf_drop(b, (int)(de & 15u)); ds = (int)(de >> 4); }
-        else ds = inf_decode_slow(b, s.dcount, s.dsym);
-        if (ds < 0) return INF_ERR_SYMBOL;
-        const uint32_t di = k_inf_dist[ds & 31];
-        if (di == 0) return INF_ERR_SYMBOL;
-        const uint32_t dist = (di & 0xffffu) + inf_take(b, (int)(di >> 16));
-        if (dist > pos) return INF_ERR_DISTANCE;
-        if (pos + len > cap) return INF_ERR_OUTPUT;
-        if (inf_overrun(b)) return INF_ERR_INPUT;
+        uint32_t de = s.fastd[inf_peek(b, INF_DBITS)];
+        if (de) {
+            inf_drop(b, (int)(de & 15u));
+        } else {
+            const int ds = inf_decode_slow(b, s.dcount, s.dsym);
+            const uint32_t di = ds < 0 ? 0u : k_inf_dist[ds & 31];
+            if (di == 0) { rc = INF_ERR_SYMBOL; break; }
+            de = ((di >> 16) << 4) | ((di & 0xffffu) << 8);
+        }
+        const uint32_t dist = (de >> 8) + inf_take(b, (int)((de >> 4) & 15u));
+        if (dist > pos || pos + len > cap) { rc = dist > pos ? INF_ERR_DISTANCE : INF_ERR_OUTPUT; break; }
+        if (pend_at) { *pend_at = (uint8_t)pend_val; pend_at = nullptr; }
         __syncwarp();                                   // the bytes the copy reads were written by other lanes
         const uint8_t *from = out + pos - dist;
-        if (dist >= len || dist >= INF_COPY_LANES) {
+        if (len <= nl && dist >= len) {
+            // the usual case, one step: load now, store when the next match (or the end of the block) comes
+            if (lane < len) { pend_at = lane0 + pos; pend_val = *(pend_at - dist); }
+        } else if (dist >= len || dist >= INF_COPY_LANES) {
             // a step of <= 32 bytes never reads what the same step writes
             for (uint32_t k0 = 0; k0 < len; k0 += nl) {
                 const uint32_t k = k0 + lane;
@@ -281,9 +337,11 @@ __device__ __forceinline__ int inf_codes(InfBits &b, InflateScratch &s, uint8_t 
         }
         pos += len;
     }
+    if (pend_at) *pend_at = (uint8_t)pend_val;
+    return rc;
 }
 
-// Inflate one raw deflate stream src[0, src_len) into out[0, cap) (shared memory on the device); *produced = bytes written.
+// Inflate one raw deflate stream src[0, src_len) into out[0, cap) (the member's place in the text); *produced = bytes written.
 // The caller compares *produced with the announced size.
 __device__ __forceinline__ int inflate_raw_warp(const uint8_t *src, uint32_t src_len, uint8_t *out, uint32_t cap, uint32_t *produced,
                                                 InflateScratch &s, uint32_t lane, uint32_t nl)
@@ -334,11 +392,11 @@ __device__ __forceinline__ int inflate_raw_warp(const uint8_t *src, uint32_t src
                 }
                 for (; idx < 19; idx++) s.lengths[order[idx]] = 0;
                 if (inf_construct(s.lcount, s.lsym, s.lengths, 19) != 0) return INF_ERR_TABLE;   // the code-length code must be complete
-                inf_build_direct(s.lcount, s.lsym, s.fastd, INF_CBITS, lane, nl);                // its codes have at most 7 bits
+                inf_build_direct(s.lcount, s.lsym, s.u.single, INF_CBITS, lane, nl);             // its codes have at most 7 bits
                 idx = 0;
                 while (idx < nlen + ndist) {
                     inf_refill(b);
-                    const uint32_t ce = s.fastd[inf_peek(b, INF_CBITS)];
+                    const uint32_t ce = s.u.single[inf_peek(b, INF_CBITS)];
                     if (ce == 0) return INF_ERR_SYMBOL;
                     inf_drop(b, (int)(ce & 15u));
                     const int sym = (int)(ce >> 4);
@@ -361,7 +419,7 @@ __device__ __forceinline__ int inflate_raw_warp(const uint8_t *src, uint32_t src
                     if (inf_overrun(b)) return INF_ERR_INPUT;
                 }
                 if (s.lengths[256] == 0) return INF_ERR_TABLE;   // no end-of-block code
-                __syncwarp();                                     // every replica is done with the code-length table in fastd
+                __syncwarp();                                     // every replica is done with the code-length table in u.single
                 int err = inf_construct(s.lcount, s.lsym, s.lengths, nlen);
                 if (err < 0 || (err > 0 && nlen - s.lcount[0] != 1)) return INF_ERR_TABLE;   // incomplete only allowed for a single code
                 inf_build_direct(s.lcount, s.lsym, s.u.single, INF_LBITS, lane, nl);
@@ -369,7 +427,7 @@ __device__ __forceinline__ int inflate_raw_warp(const uint8_t *src, uint32_t src
                 if (err < 0 || (err > 0 && ndist - s.dcount[0] != 1)) return INF_ERR_TABLE;
             }
             inf_build_multi(s, lane, nl);
-            inf_build_direct(s.dcount, s.dsym, s.fastd, INF_DBITS, lane, nl);
+            inf_build_dist(s.dcount, s.dsym, s.fastd, lane, nl);
             const int rc = inf_codes(b, s, out, pos, cap, lane, nl);
             *produced = pos;
             if (rc) return rc;

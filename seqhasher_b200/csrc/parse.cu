@@ -493,22 +493,15 @@ __global__ void __launch_bounds__(256) fmt_write_kernel(FmtCfg c, FxOut rec, siz
 
 // ------------------------------------------------------------------------------------------- BGZF inflate
 
-// One warp (= one CTA) per BGZF member, three CTAs per SM: inflate.cuh decodes the member into a window in shared memory,
-// then the warp checks ISIZE and the CRC-32 (32 segments, combined) and stores the window to the text with 128-bit stores.
-// Members are independent by construction of the format (each is a complete gzip member of <= 64 KiB of text), so a 64 MiB
-// text chunk is ~1000 warps of work, and the compressed bytes — a third to a quarter of the text — are all that crosses PCIe.
-// The window sits at the 16-byte phase of its destination so that both sides of the final copy are aligned.
-struct BgzfSmem {
-    InflateScratch s;
-    __align__(16) uint8_t win[INF_WINDOW + 16];
-};
-
+// One warp (= one CTA) per BGZF member: inflate.cuh decodes the member straight into its place in the text, then the warp
+// checks ISIZE and the CRC-32 (32 segments, combined).  Members are independent by construction of the format (each is a
+// complete gzip member of <= 64 KiB of text), so a 64 MiB text chunk is ~1000 warps of work, and the compressed bytes — a
+// third to a quarter of the text — are all that crosses PCIe.  Only the decoder's tables are in shared memory (10 KiB), so
+// ~20 members are resident per SM and several chunks' kernels (one stream per chunk slot) share the GPU.
 __global__ void __launch_bounds__(32) bgzf_inflate_kernel(const uint8_t *__restrict__ comp, const unsigned long long *__restrict__ tab,
-                                                          size_t n_members, uint8_t *__restrict__ text,
-                                                          unsigned long long *__restrict__ status)
+                                                          size_t n_members, uint8_t *text, unsigned long long *__restrict__ status)
 {
-    extern __shared__ __align__(16) uint8_t bgzf_smem[];
-    BgzfSmem &m = *reinterpret_cast<BgzfSmem *>(bgzf_smem);
+    __shared__ InflateScratch scr;
     const size_t mi = blockIdx.x;
     if (mi >= n_members) return;
     const uint32_t lane = threadIdx.x;
@@ -516,26 +509,15 @@ __global__ void __launch_bounds__(32) bgzf_inflate_kernel(const uint8_t *__restr
     const uint32_t isize = (uint32_t)packed, want_crc = (uint32_t)(packed >> 32);
     int rc = INF_ERR_OUTPUT;
     if (isize <= INF_WINDOW) {
-        const uint32_t phase = (uint32_t)(out & 15ull);
         uint32_t produced = 0;
-        rc = inflate_raw_warp(comp + off, (uint32_t)clen, m.win + phase, isize, &produced, m.s, lane, 32u);
+        rc = inflate_raw_warp(comp + off, (uint32_t)clen, text + out, isize, &produced, scr, lane, 32u);
         if (rc == INF_OK && produced != isize) rc = INF_ERR_SIZE;
         __syncwarp();
         if (rc == INF_OK) {
-            crc_build_tables(m.s.u.crc, lane, 32u);
-            const uint32_t c = __reduce_xor_sync(0xffffffffu, crc_lane_share(m.win, phase, isize, m.s.u.crc, lane, 32u));
+            crc_build_tables(scr.u.crc, lane, 32u);
+            const uint32_t phase = (uint32_t)(out & 15ull);           // the CRC reads aligned words: start from the 16-byte line
+            const uint32_t c = __reduce_xor_sync(0xffffffffu, crc_lane_share(text + (out - phase), phase, isize, scr.u.crc, lane, 32u));
             if (c != want_crc) rc = INF_ERR_CRC;
-        }
-        if (rc == INF_OK) {
-            uint8_t *gbase = text + (out - phase);                    // 16-byte aligned: text is, and out - phase is a multiple of 16
-            const uint32_t end = phase + isize;
-            for (uint32_t u = lane * 16u; u < end; u += 32u * 16u) {
-                if (u >= phase && u + 16u <= end) {
-                    *reinterpret_cast<uint4 *>(gbase + u) = *reinterpret_cast<const uint4 *>(m.win + u);
-                } else {                                              // the first / last unit is shared with the neighbouring member
-                    for (uint32_t k = (u > phase ? u : phase); k < (u + 16u < end ? u + 16u : end); k++) gbase[k] = m.win[k];
-                }
-            }
         }
     }
     if (rc != INF_OK && lane == 0) atomicMin(status, ((unsigned long long)(mi + 1) << 8) | (unsigned)rc);
@@ -546,15 +528,7 @@ cudaError_t launch_bgzf_inflate(const uint8_t *comp, const unsigned long long *t
 {
     cudaError_t e = cudaMemsetAsync(status, 0xff, sizeof(unsigned long long), st);   // "no failure" = the largest value (atomicMin)
     if (e != cudaSuccess || n_members == 0) return e;
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        e = cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BgzfSmem));
-        if (e != cudaSuccess) return e;
-        attr_set[dev] = true;
-    }
-    bgzf_inflate_kernel<<<(unsigned)n_members, 32, sizeof(BgzfSmem), st>>>(comp, tab, n_members, text, status);
+    bgzf_inflate_kernel<<<(unsigned)n_members, 32, 0, st>>>(comp, tab, n_members, text, status);
     g_launches++;
     return cudaGetLastError();
 }

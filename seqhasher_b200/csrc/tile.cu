@@ -256,6 +256,19 @@ __global__ void __launch_bounds__(128) hash_tile_kernel(const uint8_t *__restric
     }
 }
 
+// largest dynamic shared memory a block may opt into on this kind of device (227 KiB on sm_100)
+static int max_optin_smem()
+{
+    static int v = 0;
+    if (v == 0) {
+        int dev = 0, got = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&got, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || got <= 0) got = 232448;
+        v = got;
+    }
+    return v;
+}
+
 template <uint32_t MASK, bool UPPER, bool STRIP>
 static cudaError_t launch_tile_k(const uint8_t *res, const int64_t *offs, size_t n, const OutPtrs &out, uint32_t rmask,
                                  uint32_t cap, uint8_t *strip_scratch, int64_t *out_len, cudaStream_t st)
@@ -263,7 +276,18 @@ static cudaError_t launch_tile_k(const uint8_t *res, const int64_t *offs, size_t
     const unsigned threads = 128;
     const size_t blocks = (n + threads - 1) / threads;
     const size_t smem = (size_t)cap + 32;
-    cudaError_t e = cudaFuncSetAttribute(hash_tile_kernel<MASK, UPPER, STRIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // The limit is a property of the function, shared by every host thread that launches it (the chunk slots of the compiled
+    // host do, with windows of different sizes): always ask for the device's maximum, so that concurrent callers set the same
+    // value and no launch can meet a limit another thread has just lowered.
+    static int dyn_max = 0;   // per instantiation: the opt-in maximum less the kernel's static shared memory (same value from every thread)
+    if (dyn_max == 0) {
+        cudaFuncAttributes fa;
+        cudaError_t ea = cudaFuncGetAttributes(&fa, hash_tile_kernel<MASK, UPPER, STRIP>);
+        if (ea != cudaSuccess) return ea;
+        dyn_max = max_optin_smem() - (int)fa.sharedSizeBytes;
+    }
+    if (smem > (size_t)dyn_max) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(hash_tile_kernel<MASK, UPPER, STRIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max);
     if (e != cudaSuccess) return e;
     hash_tile_kernel<MASK, UPPER, STRIP><<<(unsigned)blocks, threads, smem, st>>>(res, offs, n, out, rmask, cap, strip_scratch, out_len);
     g_launches++;
