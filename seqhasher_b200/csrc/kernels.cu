@@ -304,10 +304,17 @@ cudaError_t launch_length_sort(const int64_t *offs, size_t n, void *perm_and_tmp
 // Normalise pre-pass.  Byte block b covers [b*4096, (b+1)*4096); thread t of the CTA owns the 16
 // bytes at b*4096 + 16*t.
 
+// nonzero iff some byte of w is below 0x21 (the classic "has a byte less than n" test: exact as an any-test)
+__device__ __forceinline__ uint32_t any_below_0x21(uint32_t w) { return (w - 0x21212121u) & ~w & 0x80808080u; }
+
 // bit j of the result = byte j of the 16-byte chunk is kept (inside the buffer and not whitespace)
 template <bool STRIP>
 __device__ __forceinline__ uint32_t keep_mask16(const uint4 &v, size_t pos, size_t total)
 {
+    // sequence bytes are letters: unless some byte is below 0x21 nothing can be whitespace, and the byte-wise test (a hundred
+    // instructions per chunk) is skipped — it made the pre-pass ALU-bound at a third of the memory rate
+    if (pos + 16 <= total && (!STRIP || (any_below_0x21(v.x) | any_below_0x21(v.y) | any_below_0x21(v.z) | any_below_0x21(v.w)) == 0u))
+        return 0xffffu;
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t m = 0;
 #pragma unroll
@@ -465,14 +472,35 @@ template <bool STRIP, bool UPPER>
 __global__ void __launch_bounds__(256) compact_kernel(const uint8_t *__restrict__ res, size_t total,
                                                       const int64_t *__restrict__ offs, size_t n,
                                                       const int64_t *__restrict__ block_prefix,
-                                                      uint8_t *__restrict__ out_res, int64_t *__restrict__ out_offs)
+                                                      uint8_t *__restrict__ out_res, int64_t *__restrict__ out_offs,
+                                                      size_t nb, size_t per_cta)
 {
+    // A CTA takes per_cta CONSECUTIVE 4 KiB blocks: the record boundaries that fall into them are consecutive entries of offs,
+    // so one binary search per CTA finds the first and the rest is a walk.  (One block per CTA with its own search was 23
+    // dependent loads of latency per 4 KiB: 15 of the 78 ms of config C5, profiles/r02_launches_c5_before_prepass.csv.)
     __shared__ uint32_t s_excl[256];
     __shared__ uint32_t s_mask[256];
     __shared__ uint32_t s_w[8];
-    const size_t bstart = (size_t)blockIdx.x * NORM_BLK;
+    __shared__ __align__(16) uint8_t s_out[NORM_BLK + 32];
+    __shared__ uint4 s_last[8];                                    // every warp's last unit, for the next warp's first lane
+    const size_t blk0 = (size_t)blockIdx.x * per_cta, blk1 = blk0 + per_cta < nb ? blk0 + per_cta : nb;
+    if (blk0 >= blk1) return;
+    size_t cur = 0;                                                // first i with offs[i] >= start of the CTA's first block
+    {
+        size_t lo = 0, hi = n + 1;
+        const size_t first = blk0 * NORM_BLK;
+        while (lo < hi) {
+            size_t mid = (lo + hi) >> 1;
+            if ((size_t)offs[mid] < first) lo = mid + 1; else hi = mid;
+        }
+        cur = lo;
+    }
+    uint4 vnext = load16_guarded(res, blk0 * NORM_BLK + 16u * threadIdx.x, total);
+  for (size_t blk = blk0; blk < blk1; blk++) {
+    const size_t bstart = blk * NORM_BLK;
     const size_t pos = bstart + 16u * threadIdx.x;
-    const uint4 v = load16_guarded(res, pos, total);
+    const uint4 v = vnext;
+    if (blk + 1 < blk1) vnext = load16_guarded(res, pos + NORM_BLK, total);   // the next block's bytes are on their way
     const uint32_t mask = keep_mask16<STRIP>(v, pos, total);
     const uint32_t cnt = __popc(mask);
     uint32_t incl = cnt;
@@ -488,12 +516,10 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint8_t *__restrict_
     const uint32_t excl = wbase + incl - cnt;
     s_excl[threadIdx.x] = excl;
     s_mask[threadIdx.x] = mask;
-    const int64_t bp = block_prefix[blockIdx.x];
+    const int64_t bp = block_prefix[blk];
     // The block's kept bytes form one contiguous run out_res[bp, bp + blk_total).  They are compacted in shared memory at the
     // same 16-byte phase as their destination and copied out with aligned 128-bit stores (byte stores straight to global
     // memory made this kernel 0.85 TB/s: 17.9 of the 83.7 ms of config C5, profiles/r02_launches_bench.csv).
-    __shared__ __align__(16) uint8_t s_out[NORM_BLK + 32];
-    __shared__ uint4 s_last[8];                                    // every warp's last unit, for the next warp's first lane
     const uint32_t phase = (uint32_t)(bp & 15);
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
     if (UPPER) {
@@ -576,19 +602,21 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint8_t *__restrict_
         }
     }
     __syncthreads();
-    // record boundaries that fall inside this byte block: offs[i] in [bstart, bstart + 4096)
-    size_t lo = 0, hi = n + 1;   // first i with offs[i] >= bstart
-    while (lo < hi) {
-        size_t mid = (lo + hi) >> 1;
-        if ((size_t)offs[mid] < bstart) lo = mid + 1; else hi = mid;
+    // record boundaries that fall inside this byte block: offs[i] in [bstart, bstart + 4096), i = cur, cur + 1, ...
+    while (true) {
+        const size_t i = cur + threadIdx.x;
+        const size_t p = i <= n ? (size_t)offs[i] : ~(size_t)0;
+        const bool inside = p < bstart + NORM_BLK;
+        if (inside) {
+            const uint32_t rel = (uint32_t)(p - bstart);
+            const uint32_t t = rel >> 4, within = rel & 15u;
+            out_offs[i] = bp + s_excl[t] + __popc(s_mask[t] & ((1u << within) - 1u));
+        }
+        const int got = __syncthreads_count(inside);               // also the barrier before the shared arrays are rewritten
+        cur += (size_t)got;
+        if (got < (int)blockDim.x) break;
     }
-    for (size_t i = lo + threadIdx.x; i <= n; i += blockDim.x) {
-        const size_t p = (size_t)offs[i];
-        if (p >= bstart + NORM_BLK) break;
-        const uint32_t rel = (uint32_t)(p - bstart);
-        const uint32_t t = rel >> 4, within = rel & 15u;
-        out_offs[i] = bp + s_excl[t] + __popc(s_mask[t] & ((1u << within) - 1u));
-    }
+  }
 }
 
 __global__ void lengths_kernel(const int64_t *__restrict__ offs, size_t n, int64_t *__restrict__ out_len)
@@ -634,14 +662,19 @@ cudaError_t launch_normalise(const uint8_t *res, const int64_t *offs, size_t n, 
         cudaError_t es = scan_counts(block_counts, nb, block_prefix, scan_tmp, st);
         if (es != cudaSuccess) return es;
     }
+    // persistent grid: every CTA walks a run of consecutive blocks (at least 16, so that the one binary search per CTA is noise)
+    size_t ctas = 148u * 8u;
+    size_t per_cta = (nb + ctas - 1) / ctas;
+    if (per_cta < 16) per_cta = 16;
+    ctas = (nb + per_cta - 1) / per_cta;
     if (strip && upper)
-        compact_kernel<true, true><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs);
+        compact_kernel<true, true><<<(unsigned)ctas, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs, nb, per_cta);
     else if (strip)
-        compact_kernel<true, false><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs);
+        compact_kernel<true, false><<<(unsigned)ctas, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs, nb, per_cta);
     else if (upper)
-        compact_kernel<false, true><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs);
+        compact_kernel<false, true><<<(unsigned)ctas, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs, nb, per_cta);
     else
-        compact_kernel<false, false><<<(unsigned)nb, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs);
+        compact_kernel<false, false><<<(unsigned)ctas, 256, 0, st>>>(res, total_bytes, offs, n, block_prefix, out_res, out_offs, nb, per_cta);
     g_launches += 2;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
