@@ -662,8 +662,17 @@ cudaError_t launch_normalise(const uint8_t *res, const int64_t *offs, size_t n, 
         cudaError_t es = scan_counts(block_counts, nb, block_prefix, scan_tmp, st);
         if (es != cudaSuccess) return es;
     }
-    // persistent grid: every CTA walks a run of consecutive blocks (at least 16, so that the one binary search per CTA is noise)
-    size_t ctas = 148u * 8u;
+    // persistent grid: exactly the CTAs that are resident at once (one more per SM would run as a second, short wave), every CTA
+    // walking a run of consecutive blocks (at least 16, so that the one binary search per CTA is noise)
+    static int resident = 0;
+    if (resident == 0) {
+        int occ = 0, sms = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, compact_kernel<true, true>, 256, 0);
+        resident = (occ > 0 ? occ : 4) * (sms > 0 ? sms : 148);
+    }
+    size_t ctas = (size_t)resident;
     size_t per_cta = (nb + ctas - 1) / ctas;
     if (per_cta < 16) per_cta = 16;
     ctas = (nb + per_cta - 1) / per_cta;

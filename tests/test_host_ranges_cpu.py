@@ -25,6 +25,8 @@ def lib():
     L.emul_find_cut.restype = ctypes.c_size_t
     L.emul_find_record_start.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
     L.emul_find_record_start.restype = ctypes.c_size_t
+    L.emul_scan_bgzf.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
+    L.emul_scan_bgzf.restype = ctypes.c_long
     return L
 
 
@@ -86,3 +88,40 @@ def test_cut_is_the_start_of_the_last_record(lib, fastq):
                     assert got == full[-1] or got in inside
             else:
                 assert got == (inside[-1] if inside else 0), (trial, n, got)
+
+
+def test_bgzf_member_walk_of_the_compiled_host_equals_the_python_scanner(lib, tmp_path):
+    """scan_bgzf (csrc/host/main.cpp: one pread per member) against seqhasher_b200.host.bgzf.scan_members on BGZF files of
+    several member sizes, with an extra subfield in front of 'BC', and on files that must be refused."""
+    import gzip
+    import struct
+    import zlib
+    from seqhasher_b200.host import bgzf
+    rng = np.random.default_rng(4)
+    data = rng.choice(np.frombuffer(b"ACGT\n", dtype=np.uint8), size=700_000).tobytes()
+    out = np.zeros(4 * 20000, dtype=np.uint64)
+
+    def walk(blob):
+        f = tmp_path / "x.gz"
+        f.write_bytes(blob)
+        return lib.emul_scan_bgzf(str(f).encode(), out.ctypes.data, 20000)
+    for block, level in ((65280, 6), (65536, 1), (1000, 6), (37, 9), (65536, 0)):
+        gz = bgzf.compress(data if block > 100 else data[:20000], level, block)
+        want = bgzf.scan_members(gz)
+        n = walk(gz)
+        assert n == len(want)
+        got = out[:4 * n].reshape(n, 4)
+        assert (got[:, 0] == want[:, 3]).all() and (got[:, 1:4] == want[:, 0:3]).all()
+    # an extra subfield before the BC one (the spec allows it)
+    piece = data[:5000]
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    cdata = c.compress(piece) + c.flush()
+    extra = b"XY\x03\x00abc" + b"BC\x02\x00" + struct.pack("<H", 12 + 13 + len(cdata) + 8 - 1)
+    member = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", len(extra)) + extra + cdata + struct.pack("<II", zlib.crc32(piece), len(piece))
+    assert gzip.decompress(member) == piece
+    assert walk(member + bgzf.EOF_MEMBER) == 2 and int(out[1]) == 12 + 13 and int(out[2]) == len(cdata)
+    assert bgzf.scan_members(member + bgzf.EOF_MEMBER) is not None
+    good = bgzf.compress(data[:100000], 6, 5000)
+    for bad in (gzip.compress(data[:1000]), good + gzip.compress(b"tail"), good[:-5], good + b"\x00", good[:17]):
+        assert walk(bad) == -1
+        assert bgzf.scan_members(bad) is None
