@@ -133,3 +133,47 @@ def test_device_crc32_lane_shares_match_zlib(inflate_emul):
         buf[:] = rng.integers(0, 256, size=buf.size)
         got = inflate_emul.emul_crc32_lanes(base, first, n)
         assert got == zlib.crc32(buf[first:first + n].tobytes()), (trial, first, n)
+
+
+def test_nthash_bit_planes_equal_the_seed_table_fold():
+    """hash_nt_planes.cuh (the warp kernel's look-up-free path): a unit is accepted iff all 16 bytes are ACGTU in either case,
+    and the planes of any number of accepted units expand to XOR_units XOR_j rol(seed[byte j], 15 - j)."""
+    so = os.path.join(HERE, "emul", "_build", "libnt_planes_emul.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-I" + os.path.join(HERE, "emul"),
+                    "-I" + os.path.join(ROOT, "seqhasher_b200", "csrc"), "-o", so, os.path.join(HERE, "emul", "nt_planes_emul.cpp")], check=True)
+    L = ctypes.CDLL(so)
+    L.emul_nt_planes.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+    L.emul_nt_planes.restype = ctypes.c_uint64
+    L.emul_nt_seed.argtypes = [ctypes.c_uint32]
+    L.emul_nt_seed.restype = ctypes.c_uint64
+    seed = [L.emul_nt_seed(c) for c in range(256)]
+    bases = set(b"ACGTUacgtu")
+    assert all((seed[c] != 0) == (c in bases or c in (1, 3, 4, 5, 7)) for c in range(256))
+    M = (1 << 64) - 1
+
+    def rol(x, r):
+        return ((x << r) | (x >> (64 - r))) & M if r else x
+    rng = np.random.default_rng(11)
+    al_clean = np.frombuffer(b"ACGTacgtUu", dtype=np.uint8)
+    for trial in range(1500):
+        n = int(rng.integers(1, 40))
+        units = rng.choice(al_clean, size=16 * n).astype(np.uint8)
+        kind = trial % 3
+        if kind == 1:      # a few arbitrary bytes: those units must be refused
+            for _ in range(int(rng.integers(1, 4))):
+                units[int(rng.integers(0, 16 * n))] = int(rng.integers(0, 256))
+        elif kind == 2:    # bytes one bit away from a base, N, IUPAC codes, control bytes with a seed
+            for _ in range(int(rng.integers(1, 6))):
+                units[int(rng.integers(0, 16 * n))] = int(rng.choice(np.frombuffer(b"NnRYKMSWBDHV@EFDPQRSVW`\x01\x03\x04\x05\x07\x00\x80\xc1 -", dtype=np.uint8)))
+        valid = np.zeros(n, dtype=np.uint8)
+        got = L.emul_nt_planes(units.ctypes.data, n, valid.ctypes.data)
+        want = 0
+        for i in range(n):
+            u = units[16 * i:16 * i + 16].tolist()
+            ok = all(c in bases for c in u)
+            assert bool(valid[i]) == ok, (trial, i, bytes(u))
+            if ok:
+                for j, c in enumerate(u):
+                    want ^= rol(seed[c], 15 - j)
+        assert got == want, trial
