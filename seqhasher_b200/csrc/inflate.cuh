@@ -13,8 +13,8 @@
 // nothing (a warp instruction takes one issue slot whatever the lane count) and it leaves every lane with the decoder state,
 // so the parts that ARE parallel need no hand-over:
 //   * a match (length, distance) is copied by the lanes side by side, 32 bytes per step, straight in the text buffer (global
-//     memory; a BGZF member never reaches behind its own first byte).  The store of a copy is held back until the next match is
-//     decoded, so the load's L2 round trip overlaps ~60 instructions of Huffman decoding instead of stalling the warp;
+//     memory; a BGZF member never reaches behind its own first byte).  A short copy is carried into the next turn of the decode
+//     loop — load at the top, store at the bottom — so the load's L2 round trip runs under the decoding of the next symbol;
 //   * the literal/length table holds up to three literals per 10-bit look-up (DNA text: A/C/G/T get 2-3-bit codes), written by
 //     lanes 0..2 at once; the table is built lane-parallel from the per-code table;
 //   * the CRC-32 of the finished text is computed by 32 lanes on 32 segments, combined with the x^(8n) mod P operator (the
@@ -263,81 +263,111 @@ __device__ __forceinline__ void inf_build_multi(InflateScratch &s, uint32_t lane
 // the symbols of one block, tables in s; out[0, cap) is the member's text
 __device__ __forceinline__ int inf_codes(InfBits &b, InflateScratch &s, uint8_t *out, uint32_t &pos, uint32_t cap, uint32_t lane, uint32_t nl)
 {
-    // the held-back store of the last short copy (this lane's byte)
-    uint8_t *pend_at = nullptr;
-    uint32_t pend_val = 0;
+    // A short copy (one step, source and destination apart) is split over two turns of the loop: its load is issued at the top
+    // of the NEXT turn and its store sits at the bottom of that turn, so the L2 round trip of the load runs under the decoding
+    // of the next symbol (~40 instructions) instead of stalling the warp.  have / p_len are the same in every lane.
+    bool have = false;
+    uint32_t p_len = 0, pv = 0;
+    uint8_t *p_dst = nullptr;
+    const uint8_t *p_src = nullptr;
     int rc = -1;
     uint8_t *lane0 = out + lane;                        // this lane's column of the text: one 64-bit add per access
     INF_OPAQUE(lane0);
     while (rc < 0) {
         inf_refill(b);
+        if (have) {
+            __syncwarp();                               // the bytes the copy reads were written by other lanes
+            if (lane < p_len) pv = *p_src;
+        }
         const uint32_t e = s.multi[inf_peek(b, INF_LBITS)];
         const uint32_t kind = (e >> 4) & 7u;
-        uint32_t len, extra;
-        if (kind == 4u) {                               // a length symbol: the usual case in text that compresses
-            inf_drop(b, (int)(e & 15u));
-            len = (e >> 8) & 0x1ffu;
-            extra = (e >> 17) & 7u;
+        uint32_t len = 0, dist = 0;                     // len != 0: a match was decoded
+        if (kind == 4u || kind == 0u) {
+            uint32_t extra;
+            bool is_len = true;
+            if (kind == 4u) {                           // a length symbol: the usual case in text that compresses
+                inf_drop(b, (int)(e & 15u));
+                len = (e >> 8) & 0x1ffu;
+                extra = (e >> 17) & 7u;
+            } else {                                    // a code longer than the table's index
+                const int v = inf_decode_slow(b, s.lcount, s.lsym);
+                extra = 0;
+                if (v < 0) { rc = INF_ERR_SYMBOL; is_len = false; }
+                else if (v < 256) {
+                    is_len = false;
+                    if (pos >= cap) rc = INF_ERR_OUTPUT;
+                    else { if (lane == 0) out[pos] = (uint8_t)v; pos++; }
+                } else if (v == 256) { rc = inf_overrun(b) ? INF_ERR_INPUT : INF_OK; is_len = false; }
+                else {
+                    const uint32_t li = k_inf_len[(uint32_t)(v - 256) & 31u];
+                    if (li == 0) { rc = INF_ERR_SYMBOL; is_len = false; }
+                    len = li & 0xffffu;
+                    extra = li >> 16;
+                }
+            }
+            if (is_len) {
+                len += inf_take(b, (int)extra);
+                inf_refill(b);
+                uint32_t de = s.fastd[inf_peek(b, INF_DBITS)];
+                if (de) {
+                    inf_drop(b, (int)(de & 15u));
+                } else {
+                    const int ds = inf_decode_slow(b, s.dcount, s.dsym);
+                    const uint32_t di = ds < 0 ? 0u : k_inf_dist[ds & 31];
+                    if (di == 0) rc = INF_ERR_SYMBOL;
+                    de = ((di >> 16) << 4) | ((di & 0xffffu) << 8);
+                }
+                dist = (de >> 8) + inf_take(b, (int)((de >> 4) & 15u));
+                if (rc < 0 && (dist > pos || pos + len > cap)) rc = dist > pos ? INF_ERR_DISTANCE : INF_ERR_OUTPUT;
+                if (rc >= 0) len = 0;
+            } else {
+                len = 0;
+            }
         } else if (kind - 1u < 3u) {
-            if (pos + kind > cap) { rc = INF_ERR_OUTPUT; break; }
-            for (uint32_t l = lane; l < kind; l += nl) lane0[pos + l - lane] = (uint8_t)(e >> (8u + 8u * l));
-            pos += kind;
-            inf_drop(b, (int)(e & 15u));
-            continue;
+            if (pos + kind > cap) rc = INF_ERR_OUTPUT;
+            else {
+                for (uint32_t l = lane; l < kind; l += nl) lane0[pos + l - lane] = (uint8_t)(e >> (8u + 8u * l));
+                pos += kind;
+                inf_drop(b, (int)(e & 15u));
+            }
         } else if (kind == 5u) {
             inf_drop(b, (int)(e & 15u));
             rc = inf_overrun(b) ? INF_ERR_INPUT : INF_OK;
-            break;
-        } else if (kind == 6u) {
+        } else {
             rc = INF_ERR_SYMBOL;
-            break;
-        } else {
-            const int v = inf_decode_slow(b, s.lcount, s.lsym);
-            if (v < 0) { rc = INF_ERR_SYMBOL; break; }
-            if (v < 256) {
-                if (pos >= cap) { rc = INF_ERR_OUTPUT; break; }
-                if (lane == 0) out[pos] = (uint8_t)v;
-                pos++;
-                continue;
+        }
+        // bottom of the turn: the held-back copy lands, then this turn's match (if any) is copied or held back in its place
+        if (have) {
+            if (lane < p_len) *p_dst = (uint8_t)pv;
+            have = false;
+        }
+        if (len) {
+            if (len <= nl && dist >= len) {
+                have = true;
+                p_len = len;
+                p_dst = lane0 + pos;
+                p_src = p_dst - dist;
+            } else {
+                __syncwarp();                           // the bytes the copy reads were written by other lanes
+                const uint8_t *from = out + pos - dist;
+                if (dist >= len || dist >= INF_COPY_LANES) {
+                    // a step of <= 32 bytes never reads what the same step writes
+                    for (uint32_t k0 = 0; k0 < len; k0 += nl) {
+                        const uint32_t k = k0 + lane;
+                        if (k < len) out[pos + k] = from[k];
+                        if (dist < len) __syncwarp();
+                    }
+                } else {
+                    for (uint32_t k = lane; k < len; k += nl) out[pos + k] = from[k % dist];   // the period repeats, as the format wants
+                }
             }
-            if (v == 256) { rc = inf_overrun(b) ? INF_ERR_INPUT : INF_OK; break; }
-            const uint32_t li = k_inf_len[(uint32_t)(v - 256) & 31u];
-            if (li == 0) { rc = INF_ERR_SYMBOL; break; }
-            len = li & 0xffffu;
-            extra = li >> 16;
+            pos += len;
         }
-        len += inf_take(b, (int)extra);
-        inf_refill(b);
-        uint32_t de = s.fastd[inf_peek(b, INF_DBITS)];
-        if (de) {
-            inf_drop(b, (int)(de & 15u));
-        } else {
-            const int ds = inf_decode_slow(b, s.dcount, s.dsym);
-            const uint32_t di = ds < 0 ? 0u : k_inf_dist[ds & 31];
-            if (di == 0) { rc = INF_ERR_SYMBOL; break; }
-            de = ((di >> 16) << 4) | ((di & 0xffffu) << 8);
-        }
-        const uint32_t dist = (de >> 8) + inf_take(b, (int)((de >> 4) & 15u));
-        if (dist > pos || pos + len > cap) { rc = dist > pos ? INF_ERR_DISTANCE : INF_ERR_OUTPUT; break; }
-        if (pend_at) { *pend_at = (uint8_t)pend_val; pend_at = nullptr; }
-        __syncwarp();                                   // the bytes the copy reads were written by other lanes
-        const uint8_t *from = out + pos - dist;
-        if (len <= nl && dist >= len) {
-            // the usual case, one step: load now, store when the next match (or the end of the block) comes
-            if (lane < len) { pend_at = lane0 + pos; pend_val = *(pend_at - dist); }
-        } else if (dist >= len || dist >= INF_COPY_LANES) {
-            // a step of <= 32 bytes never reads what the same step writes
-            for (uint32_t k0 = 0; k0 < len; k0 += nl) {
-                const uint32_t k = k0 + lane;
-                if (k < len) out[pos + k] = from[k];
-                if (dist < len) __syncwarp();
-            }
-        } else {
-            for (uint32_t k = lane; k < len; k += nl) out[pos + k] = from[k % dist];   // the period repeats, as the format wants
-        }
-        pos += len;
     }
-    if (pend_at) *pend_at = (uint8_t)pend_val;
+    if (have) {                                         // the block ended right behind a short copy
+        __syncwarp();
+        if (lane < p_len) *p_dst = *p_src;
+    }
     return rc;
 }
 
