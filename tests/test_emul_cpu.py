@@ -177,3 +177,15 @@ def test_nthash_bit_planes_equal_the_seed_table_fold():
                 for j, c in enumerate(u):
                     want ^= rol(seed[c], 15 - j)
         assert got == want, trial
+
+
+def test_device_inflate_survives_damaged_streams_under_asan():
+    """tests/emul/inflate_fuzz.cpp: the decoder on garbage, bit-flipped and truncated streams with wrong announced sizes, built
+    with -fsanitize=address,undefined and exact-size buffers: it may refuse, it must never read or write outside them."""
+    exe = os.path.join(HERE, "emul", "_build", "inflate_fuzz")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-w",
+                    "-I" + os.path.join(HERE, "emul"), "-I" + os.path.join(ROOT, "seqhasher_b200", "csrc"),
+                    os.path.join(HERE, "emul", "inflate_fuzz.cpp"), "-lz", "-o", exe], check=True)
+    p = subprocess.run([exe, "40000"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "no memory error" in p.stdout, p.stdout[-500:] + p.stderr[-2000:]
