@@ -18,17 +18,17 @@ MAX_ISIZE = 65536
 EOF_MEMBER = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
-def compress(data: bytes, level: int = 6, block: int = 65280, eof_marker: bool = True) -> bytes:
-    """`data` as a BGZF file: one member per `block` bytes of text (bgzip uses 65280), raw DEFLATE at `level`."""
+def compress(data: bytes, level: int = 6, block: int = 65280, eof_marker: bool = True, strategy: int = zlib.Z_DEFAULT_STRATEGY) -> bytes:
+    """`data` as a BGZF file: one member per `block` bytes of text (bgzip uses 65280), raw DEFLATE at `level` / `strategy`."""
     assert 1 <= block <= MAX_ISIZE
     out = []
     for i in range(0, len(data), block):
         piece = data[i:i + block]
-        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
         cdata = c.compress(piece) + c.flush()
         bsize = 12 + 6 + len(cdata) + 8 - 1
         if bsize > 0xffff:   # incompressible input at level 0 can outgrow the 16-bit size field: halve the block
-            out.append(compress(piece, level, max(block // 2, 1), eof_marker=False))
+            out.append(compress(piece, level, max(block // 2, 1), eof_marker=False, strategy=strategy))
             continue
         out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + cdata +
                    struct.pack("<II", zlib.crc32(piece), len(piece)))
