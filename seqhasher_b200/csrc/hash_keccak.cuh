@@ -28,6 +28,19 @@ __device__ __forceinline__ uint64_t rol64c(uint64_t x)
     return mk64(__funnelshift_l(lo, hi, R - 32), __funnelshift_l(hi, lo, R - 32));
 }
 
+// a ^ b ^ c on 64 bits as two three-input LOP3 (ptxas does not merge the XORs of a value that has several uses)
+__device__ __forceinline__ uint64_t xor3_64(uint64_t a, uint64_t b, uint64_t c)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t lo, hi;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(lo) : "r"((uint32_t)a), "r"((uint32_t)b), "r"((uint32_t)c));
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(hi) : "r"((uint32_t)(a >> 32)), "r"((uint32_t)(b >> 32)), "r"((uint32_t)(c >> 32)));
+    return mk64(lo, hi);
+#else
+    return a ^ b ^ c;
+#endif
+}
+
 // Keccak-p[1600, NR]: the last NR rounds of Keccak-f.  Lane A[x][y] is a[x + 5*y].
 template <int NR>
 __device__ __forceinline__ void keccak_p(uint64_t (&a)[25])
@@ -39,34 +52,45 @@ __device__ __forceinline__ void keccak_p(uint64_t (&a)[25])
         uint64_t c2 = a[2] ^ a[7] ^ a[12] ^ a[17] ^ a[22];
         uint64_t c3 = a[3] ^ a[8] ^ a[13] ^ a[18] ^ a[23];
         uint64_t c4 = a[4] ^ a[9] ^ a[14] ^ a[19] ^ a[24];
-        uint64_t d0 = c4 ^ rol64c<1>(c1), d1 = c0 ^ rol64c<1>(c2), d2 = c1 ^ rol64c<1>(c3);
-        uint64_t d3 = c2 ^ rol64c<1>(c4), d4 = c3 ^ rol64c<1>(c0);
+        // theta's D[x] = C[x-1] ^ rol(C[x+1], 1) is never formed: a ^ C[x-1] ^ rol(C[x+1], 1) is ONE three-input LOP3 per
+        // half, the same count as a ^ D, so the ten LOP3 of the D's are saved (5 % of the round's ALU-pipe instructions)
+        const uint64_t r0 = rol64c<1>(c0), r1 = rol64c<1>(c1), r2 = rol64c<1>(c2), r3 = rol64c<1>(c3), r4 = rol64c<1>(c4);
+#define KD0(x) xor3_64(x, c4, r1)
+#define KD1(x) xor3_64(x, c0, r2)
+#define KD2(x) xor3_64(x, c1, r3)
+#define KD3(x) xor3_64(x, c2, r4)
+#define KD4(x) xor3_64(x, c3, r0)
         // theta + rho + pi: b[y][(2x+3y)%5] = rol(a[x][y] ^ d[x], r[x][y])
-        uint64_t b0 = a[0] ^ d0;
-        uint64_t b10 = rol64c<1>(a[1] ^ d1);
-        uint64_t b20 = rol64c<62>(a[2] ^ d2);
-        uint64_t b5 = rol64c<28>(a[3] ^ d3);
-        uint64_t b15 = rol64c<27>(a[4] ^ d4);
-        uint64_t b16 = rol64c<36>(a[5] ^ d0);
-        uint64_t b1 = rol64c<44>(a[6] ^ d1);
-        uint64_t b11 = rol64c<6>(a[7] ^ d2);
-        uint64_t b21 = rol64c<55>(a[8] ^ d3);
-        uint64_t b6 = rol64c<20>(a[9] ^ d4);
-        uint64_t b7 = rol64c<3>(a[10] ^ d0);
-        uint64_t b17 = rol64c<10>(a[11] ^ d1);
-        uint64_t b2 = rol64c<43>(a[12] ^ d2);
-        uint64_t b12 = rol64c<25>(a[13] ^ d3);
-        uint64_t b22 = rol64c<39>(a[14] ^ d4);
-        uint64_t b23 = rol64c<41>(a[15] ^ d0);
-        uint64_t b8 = rol64c<45>(a[16] ^ d1);
-        uint64_t b18 = rol64c<15>(a[17] ^ d2);
-        uint64_t b3 = rol64c<21>(a[18] ^ d3);
-        uint64_t b13 = rol64c<8>(a[19] ^ d4);
-        uint64_t b14 = rol64c<18>(a[20] ^ d0);
-        uint64_t b24 = rol64c<2>(a[21] ^ d1);
-        uint64_t b9 = rol64c<61>(a[22] ^ d2);
-        uint64_t b19 = rol64c<56>(a[23] ^ d3);
-        uint64_t b4 = rol64c<14>(a[24] ^ d4);
+        uint64_t b0 = KD0(a[0]);
+        uint64_t b10 = rol64c<1>(KD1(a[1]));
+        uint64_t b20 = rol64c<62>(KD2(a[2]));
+        uint64_t b5 = rol64c<28>(KD3(a[3]));
+        uint64_t b15 = rol64c<27>(KD4(a[4]));
+        uint64_t b16 = rol64c<36>(KD0(a[5]));
+        uint64_t b1 = rol64c<44>(KD1(a[6]));
+        uint64_t b11 = rol64c<6>(KD2(a[7]));
+        uint64_t b21 = rol64c<55>(KD3(a[8]));
+        uint64_t b6 = rol64c<20>(KD4(a[9]));
+        uint64_t b7 = rol64c<3>(KD0(a[10]));
+        uint64_t b17 = rol64c<10>(KD1(a[11]));
+        uint64_t b2 = rol64c<43>(KD2(a[12]));
+        uint64_t b12 = rol64c<25>(KD3(a[13]));
+        uint64_t b22 = rol64c<39>(KD4(a[14]));
+        uint64_t b23 = rol64c<41>(KD0(a[15]));
+        uint64_t b8 = rol64c<45>(KD1(a[16]));
+        uint64_t b18 = rol64c<15>(KD2(a[17]));
+        uint64_t b3 = rol64c<21>(KD3(a[18]));
+        uint64_t b13 = rol64c<8>(KD4(a[19]));
+        uint64_t b14 = rol64c<18>(KD0(a[20]));
+        uint64_t b24 = rol64c<2>(KD1(a[21]));
+        uint64_t b9 = rol64c<61>(KD2(a[22]));
+        uint64_t b19 = rol64c<56>(KD3(a[23]));
+        uint64_t b4 = rol64c<14>(KD4(a[24]));
+#undef KD0
+#undef KD1
+#undef KD2
+#undef KD3
+#undef KD4
         // chi
         a[0] = b0 ^ (~b1 & b2);   a[1] = b1 ^ (~b2 & b3);   a[2] = b2 ^ (~b3 & b4);
         a[3] = b3 ^ (~b4 & b0);   a[4] = b4 ^ (~b0 & b1);
