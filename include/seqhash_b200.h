@@ -162,7 +162,7 @@ unsigned long long shb_launch_count(void);
 typedef struct shb_textproc shb_textproc;
 shb_textproc *shb_textproc_create(int device, size_t max_text_bytes);
 void shb_textproc_destroy(shb_textproc *t);
-uint8_t *shb_textproc_input(shb_textproc *t);
+uint8_t *shb_textproc_input(shb_textproc *t);   /* the pinned text buffer (capacity + 64 bytes), allocated by the first call; NULL on failure */
 size_t shb_textproc_capacity(shb_textproc *t);
 int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, const int *algos, int n_algos,
                      unsigned flags, int headers_only, const char *label);

@@ -596,7 +596,6 @@ shb_textproc *shb_textproc_create(int device, size_t max_text_bytes)
     const size_t nr = (size_t)t->max_records;
     bool ok = cudaSetDevice(device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaHostAlloc(&t->h_text, max_text_bytes + 64, cudaHostAllocDefault) == cudaSuccess &&
               cudaHostAlloc(&t->h_info, sizeof(shb::FxInfo) + 64, cudaHostAllocDefault) == cudaSuccess &&
               cudaMalloc(&t->d_text, max_text_bytes + 64) == cudaSuccess &&
               cudaMalloc(&t->d_res, max_text_bytes + 64) == cudaSuccess &&
@@ -636,7 +635,19 @@ void shb_textproc_destroy(shb_textproc *t)
     delete t;
 }
 
-uint8_t *shb_textproc_input(shb_textproc *t) { return t ? t->h_text : nullptr; }
+// the pinned text buffer exists from the first call on: a textproc that only ever sees BGZF members never pins it
+uint8_t *shb_textproc_input(shb_textproc *t)
+{
+    if (!t) return nullptr;
+    if (!t->h_text) {
+        if (cudaSetDevice(t->device) != cudaSuccess || cudaHostAlloc(&t->h_text, t->cap + 64, cudaHostAllocDefault) != cudaSuccess) {
+            t->h_text = nullptr;
+            fail(SHB_ERR_CUDA, std::string("textproc staging allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+            return nullptr;
+        }
+    }
+    return t->h_text;
+}
 size_t shb_textproc_capacity(shb_textproc *t) { return t ? t->cap : 0; }
 
 // The record loop on a text that is already in t->d_text (16 zero bytes behind it): split, hash, format, copy the output back.
@@ -737,6 +748,7 @@ int shb_textproc_run(shb_textproc *t, size_t n_bytes, int format, int is_final, 
     t->out_bytes = t->consumed = t->n_records = t->n_empty = t->n_nonascii = 0;
     t->dev_text_bytes = 0;
     if (n_bytes == 0) return SHB_OK;
+    if (!t->h_text) return fail(SHB_ERR_BAD_ARG, "no text staged: write the chunk into shb_textproc_input() first");
     if (is_final && t->h_text[n_bytes - 1] != '\n') t->h_text[n_bytes++] = '\n';   // the pinned buffer has 64 spare bytes
     std::memset(t->h_text + n_bytes, 0, 32);
     cudaStream_t st = t->stream;

@@ -546,12 +546,13 @@ size_t pread_full(int fd, uint8_t *dst, size_t n, size_t off)
 // in s->tp), s->err and the counters
 using ChunkFn = std::function<int(RangeSlot *, long long)>;
 
-void slot_thread(RangeSlot *s, size_t cap0, const ChunkFn *fn)
+void slot_thread(RangeSlot *s, size_t cap0, const ChunkFn *fn, bool text_staging)
 {
     // the slot's textproc is created here, on its own thread: the CUDA contexts of several devices come up side by side
     s->tp = shb_textproc_create(s->device, cap0);
-    if (s->tp) { s->cap = cap0; s->buf = shb_textproc_input(s->tp); }
+    if (s->tp) { s->cap = cap0; s->buf = text_staging ? shb_textproc_input(s->tp) : nullptr; }   // BGZF slots never pin a text buffer
     else s->err = std::string("seqhash_b200: ") + shb_last_error();
+    if (s->tp && text_staging && !s->buf) { s->err = std::string("seqhash_b200: ") + shb_last_error(); shb_textproc_destroy(s->tp); s->tp = nullptr; }
     long long seq = -1;
     while (true) {
         {
@@ -654,7 +655,7 @@ int range_chunk(RangeSlot *s, long long seq, const RunArgs *a, const RangeJob *j
     return rc;
 }
 
-int run_chunk_slots(long long nchunks, int n_gpus, size_t cap0, const ChunkFn &fn, FILE *out, const RunArgs &args, std::string &err);
+int run_chunk_slots(long long nchunks, int n_gpus, size_t cap0, const ChunkFn &fn, FILE *out, const RunArgs &args, std::string &err, bool text_staging = true);
 
 int process_file_ranges(int fd, size_t file_size, FILE *out, const Config &cfg, int n_gpus, std::string &err)
 {
@@ -703,7 +704,7 @@ int process_file_ranges(int fd, size_t file_size, FILE *out, const Config &cfg, 
 }
 
 // Chunks 0..nchunks-1 dealt round-robin to K slots (each a thread + a textproc), their outputs written in chunk order.
-int run_chunk_slots(long long nchunks, int n_gpus, size_t cap0, const ChunkFn &fn, FILE *out, const RunArgs &args, std::string &err)
+int run_chunk_slots(long long nchunks, int n_gpus, size_t cap0, const ChunkFn &fn, FILE *out, const RunArgs &args, std::string &err, bool text_staging)
 {
     // Slots: a slot's pread is one thread copying out of the page cache (5-6 GB/s) and a B200 takes ~13 GB/s of text, so one
     // GPU gets four; with more GPUs two each are enough readers, and every slot costs ~0.1 s to set up (80 MB of pinned
@@ -716,7 +717,7 @@ int run_chunk_slots(long long nchunks, int n_gpus, size_t cap0, const ChunkFn &f
     for (int k = 0; k < K; k++) {
         slots.emplace_back(new RangeSlot());
         slots[k]->device = k % n_gpus;
-        slots[k]->worker = std::thread(slot_thread, slots[k].get(), cap0, &fn);
+        slots[k]->worker = std::thread(slot_thread, slots[k].get(), cap0, &fn, text_staging);
     }
     std::mutex wmu;
     std::condition_variable wcv;
@@ -888,7 +889,7 @@ int bgzf_chunk(RangeSlot *s, long long seq, const RunArgs *a, const BgzfJob *job
             shb_textproc *t = shb_textproc_create(s->device, ncap);
             if (!t) { s->err = shb_last_error(); return -1; }
             shb_textproc_destroy(s->tp);
-            s->tp = t; s->cap = ncap; s->buf = shb_textproc_input(t);
+            s->tp = t; s->cap = ncap; s->buf = nullptr;
         }
         const size_t lo = job->m[lo_m].start, hi = job->m[e - 1].data + job->m[e - 1].clen + 8;
         uint8_t *stage = shb_textproc_bgzf_input(s->tp, hi - lo + 64);
@@ -1000,7 +1001,7 @@ int process_bgzf(BgzfJob &job, FILE *out, const Config &cfg, int n_gpus, std::st
     job.first.push_back(job.m.size());
     const long long nchunks = (long long)job.first.size() - 1;
     const ChunkFn fn = [&](RangeSlot *s, long long seq) { return bgzf_chunk(s, seq, &args, &job); };
-    return run_chunk_slots(nchunks, n_gpus, C + 65536 + 4 * job.lookahead + 4096, fn, out, args, err);
+    return run_chunk_slots(nchunks, n_gpus, C + 65536 + 4 * job.lookahead + 4096, fn, out, args, err, false);
 }
 
 // How many GPUs this run uses: SHB_GPUS if set; otherwise one per 12 GiB of a plain regular file — bringing up one more
