@@ -227,3 +227,36 @@ def test_cli_gzip_that_is_not_bgzf_still_takes_the_host_inflate(tmp_path):
     f.write_bytes(gzip.compress(text))
     p = _cli(["--headersonly", "--name", "x", str(f), "-"])
     assert p.returncode == 0 and p.stdout.count(b"\n") == 2
+
+
+def test_cli_bgzf_two_gpus_match_one(tmp_path):
+    """SHB_GPUS=2 on a BGZF file: chunks (runs of members) alternate between two devices, each inflating its own members;
+    output order = chunk order, byte-identical to one GPU and to the plain file."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    from seqhasher_b200.host import bgzf
+    rng = np.random.default_rng(31)
+    text = _fasta(rng, 20000, 30, 3000)
+    plain, gz = tmp_path / "in.fa", tmp_path / "in.fa.gz"
+    plain.write_bytes(text)
+    gz.write_bytes(bgzf.compress(text, 6))
+    args = ["--name", "in", "--hash", "sha1,blake3,nthash"]
+    want = _cli(args + [str(plain), "-"], {"SHB_GPUS": "1"})
+    assert want.returncode == 0
+    for env in ({"SHB_GPUS": "1", "SHB_CHUNK_KB": "2048"}, {"SHB_GPUS": "2", "SHB_CHUNK_KB": "2048"}, {"SHB_GPUS": "2", "SHB_CHUNK_KB": "700", "SHB_SLOTS_PER_GPU": "3"}):
+        got = _cli(args + [str(gz), "-"], env)
+        assert got.returncode == 0, got.stderr
+        assert got.stdout == want.stdout, env
+
+
+def test_textproc_run_without_staged_text_is_refused(B):
+    """The pinned text buffer is allocated by shb_textproc_input(); running a chunk that was never staged is a caller error."""
+    import ctypes
+    L = B.lib()
+    h = L.shb_textproc_create(0, 1 << 20)
+    assert h
+    ids = (ctypes.c_int * 1)(0)
+    rc = L.shb_textproc_run(h, 100, 1, 1, ids, 1, 0, 1, None)
+    assert rc == -2 and b"shb_textproc_input" in L.shb_last_error()
+    L.shb_textproc_destroy(h)
