@@ -603,7 +603,11 @@ def main():
                    "nthash": {"ms_per_step": ms_nt, "gbps": (tb + 16 * nt) / (ms_nt * 1e-3) / 1e9,
                               "roofline": {"bound": "hbm", "achieved": (tb + 16 * nt) / (ms_nt * 1e-3) / 1e9, "peak": hbm_peak * world,
                                            "unit": "GB/s", "frac": (tb + 16 * nt) / (ms_nt * 1e-3) / 1e9 / (hbm_peak * world),
-                                           "kernel": "nthash_warp_kernel"}},
+                                           "kernel": "nthash_warp_kernel (bit-plane path for units of pure ACGTU, look-ups for the rest)",
+                                           "traffic": ((traffic.get("c4_nthash_warp") or {}).get("dram_read", 0) + (traffic.get("c4_nthash_warp") or {}).get("dram_write", 0)) or None
+                                           if world == 1 and args.scale == 1.0 else None,
+                                           "traffic_measured_in_this_run": False,
+                                           "traffic_source": (traffic.get("c4_nthash_warp") or {}).get("source")}},
                    "xxh3": {"ms_per_step": ms_x3, "gbps": (tb + 16 * nt) / (ms_x3 * 1e-3) / 1e9,
                             "roofline": {"bound": "hbm", "achieved": (tb + 16 * nt) / (ms_x3 * 1e-3) / 1e9, "peak": hbm_peak * world,
                                          "unit": "GB/s", "frac": (tb + 16 * nt) / (ms_x3 * 1e-3) / 1e9 / (hbm_peak * world),
