@@ -21,6 +21,7 @@
 #include "pbzip2.hpp"
 #include "pgzip.hpp"
 #include "readahead.hpp"
+#include "pzstd.hpp"
 #include "source.hpp"
 
 namespace host {
@@ -339,7 +340,14 @@ inline std::unique_ptr<Source> open_maybe_compressed(FILE *f, bool own, bool *co
         return std::make_unique<XzSource>(std::move(fs));
     }
     if (k >= 4 && head[0] == 0x28 && head[1] == 0xb5 && head[2] == 0x2f && head[3] == 0xfd) {
-        if (threads >= 2) return std::make_unique<ReadAhead>(std::make_unique<ZstdSource>(std::move(fs)));
+        if (threads >= 2) {
+            size_t batch = (size_t)64 << 20;
+            if (const char *e = getenv("SHB_PZSTD_BATCH_KB")) {   // tests: small batches exercise the batch seams and the fallback
+                long kb = atol(e);
+                if (kb >= 1) batch = (size_t)kb << 10;
+            }
+            return std::make_unique<ReadAhead>(std::make_unique<ParallelZstdSourceT<ZstdSource>>(std::move(fs), threads, batch));
+        }
         return std::make_unique<ZstdSource>(std::move(fs));
     }
     return fs;

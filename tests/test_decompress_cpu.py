@@ -245,3 +245,73 @@ def test_bzip2_random_streams_soak():
         rc, out, err = zcat(blob, int(rng.choice([2, 4, 8])))
         assert rc == 0, (it, err)
         assert out == b"".join(parts), (it, len(out))
+
+
+# ---- zstd: frames decoded in parallel (pzstd.hpp) ----
+
+def _zstd_lib():
+    import ctypes
+    try:
+        L = ctypes.CDLL("libzstd.so.1")
+    except OSError:
+        pytest.skip("libzstd.so.1 not available")
+    L.ZSTD_compressBound.argtypes = [ctypes.c_size_t]; L.ZSTD_compressBound.restype = ctypes.c_size_t
+    L.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+    L.ZSTD_compress.restype = ctypes.c_size_t
+    L.ZSTD_isError.argtypes = [ctypes.c_size_t]; L.ZSTD_isError.restype = ctypes.c_uint
+    return L
+
+
+def zst_frame(L, data, level=3):
+    import ctypes
+    cap = L.ZSTD_compressBound(len(data))
+    buf = ctypes.create_string_buffer(cap)
+    n = L.ZSTD_compress(buf, cap, data, len(data), level)
+    assert not L.ZSTD_isError(n)
+    return buf.raw[:n]
+
+
+def zcat_zst(blob, threads=4, batch_kb=None):
+    env = dict(os.environ, SHB_DECOMP_THREADS=str(threads))
+    if batch_kb:
+        env["SHB_PZSTD_BATCH_KB"] = str(batch_kb)
+    p = subprocess.run([ZCAT, "-"], input=blob, capture_output=True, env=env, timeout=300)
+    return p.returncode, p.stdout, p.stderr.decode()
+
+
+def test_zstd_many_frames_in_parallel_equal_the_single_stream():
+    """A .zst file of many frames (pzstd, concatenated `zstd` runs): frames are delimited by their headers and decoded on
+    several threads; batch seams anywhere, frames larger than a batch and the single-frame file fall back to the streaming
+    decoder; every variant must give the same bytes as one thread."""
+    L = _zstd_lib()
+    rng = np.random.default_rng(3)
+    data = DATA[:4_000_000]
+    cuts = sorted(set([0, len(data)] + [int(x) for x in rng.integers(0, len(data), size=40)]))
+    many = b"".join(zst_frame(L, data[a:b], int(rng.integers(1, 10))) for a, b in zip(cuts, cuts[1:]))
+    one = zst_frame(L, data, 3)
+    skippable = struct.pack("<II", 0x184D2A50, 5) + b"hello"                       # a skippable frame between data frames
+    mixed = zst_frame(L, data[:1000]) + skippable + zst_frame(L, b"") + zst_frame(L, data[1000:])
+    for blob in (many, one, mixed):
+        for threads, batch_kb in ((1, None), (4, None), (4, 64), (3, 300), (8, 1)):
+            rc, out, err = zcat_zst(blob, threads, batch_kb)
+            assert rc == 0, (threads, batch_kb, err)
+            assert out == data, (threads, batch_kb, len(out))
+
+
+def test_zstd_damaged_and_truncated_multi_frame_input_fails_after_the_good_frames():
+    L = _zstd_lib()
+    data = DATA[:2_000_000]
+    frames = [zst_frame(L, data[i:i + 100_000]) for i in range(0, len(data), 100_000)]
+    blob = b"".join(frames)
+    for threads, batch_kb in ((4, None), (4, 128), (1, None)):
+        rc, out, err = zcat_zst(blob[:len(blob) - len(frames[-1]) // 2], threads, batch_kb)
+        assert rc == 1 and "EOF" in err, err
+        assert data.startswith(out) and len(out) >= 1_800_000
+        bad = bytearray(blob)
+        k = sum(len(f) for f in frames[:10]) + len(frames[10]) // 2                 # inside frame 10
+        bad[k] ^= 0xff
+        rc, out, err = zcat_zst(bytes(bad), threads, batch_kb)
+        assert rc == 1 and "zstd" in err, err
+        assert data.startswith(out)
+        rc, out, err = zcat_zst(blob + b"garbage at the end", threads, batch_kb)
+        assert rc == 1 and data.startswith(out)
