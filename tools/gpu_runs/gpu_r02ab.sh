@@ -1,4 +1,4 @@
-# usage: bash tools/gpu_r02ab.sh N   (under gpurun --gpus N): bench line + the multi-GPU CLI tests
+# usage: bash tools/gpu_runs/gpu_r02ab.sh N   (under gpurun --gpus N): bench line + the multi-GPU CLI tests
 N=$1
 set -x
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r02ab_bench_n$N.json 2> gpurun_out/r02ab_bench_n$N.err
