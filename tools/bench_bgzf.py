@@ -20,6 +20,22 @@ sys.path.insert(0, ROOT)
 ALL12 = ["sha1", "sha3", "md5", "xxhash", "xxh3", "cityhash", "murmur3", "nthash", "blake3", "k12", "rapidhash", "rapidhash32"]
 
 
+def make_fastq(nrec, seed=5):
+    """150-bp reads with Illumina-like binned qualities (mostly F, some : , #) — the literal-heavy case of the decoder"""
+    rng = np.random.default_rng(seed)
+    L = 150
+    seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=nrec * L).reshape(nrec, L)
+    q = rng.choice(np.frombuffer(b"FFFFFFFFFFFF::,#", dtype=np.uint8), size=nrec * L).reshape(nrec, L)
+    parts = []
+    for i in range(nrec):
+        parts.append(b"@A00123:45:HXXXXXXXX:1:1101:%d:%d 1:N:0:ACGTACGT\n" % (1000 + i % 30000, 1000 + i // 7))
+        parts.append(seq[i].tobytes())
+        parts.append(b"\n+\n")
+        parts.append(q[i].tobytes())
+        parts.append(b"\n")
+    return b"".join(parts)
+
+
 def make_text(nrec, seed=5):
     rng = np.random.default_rng(seed)
     lens = rng.integers(30, 3001, size=nrec)
@@ -49,12 +65,14 @@ def main():
     ap.add_argument("--hash", default="sha1")
     ap.add_argument("--no-cli", action="store_true")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--fastq", action="store_true", help="150-bp FASTQ reads instead of the C5 FASTA")
     a = ap.parse_args()
     from seqhasher_b200 import binding as B
     from seqhasher_b200.host import bgzf
     B.init(1)
     cores = os.cpu_count() or 1
-    text = make_text(a.records)
+    text = make_fastq(a.records) if a.fastq else make_text(a.records)
+    fmt = 2 if a.fastq else 1
     gz = bgzf_parallel(text, a.level, min(cores, 32))
     members = bgzf.scan_members(gz)
     out = {"records": a.records, "text_bytes": len(text), "bgzf_bytes": len(gz), "members": int(len(members)), "level": a.level,
@@ -80,7 +98,7 @@ def main():
             stage = tp.bgzf_input(40 << 20)
             stage[:hi - lo] = mv[lo:hi]
             tab = members[k:last + 1, :3].copy(); tab[:, 0] -= np.uint64(lo)
-            r = tp.run_bgzf(hi - lo, tab, n_own, extra, 0 if k == 0 else -1, last == n - 1, 1, ids, B.FLAG_UPPER, True, b"c5.fa")
+            r = tp.run_bgzf(hi - lo, tab, n_own, extra, 0 if k == 0 else -1, last == n - 1, fmt, ids, B.FLAG_UPPER, True, b"c5.fa")
             assert r is not None
             ms = tp.last_ms()
             inflate_ms += tp.last_inflate_ms(); h2d_ms += ms["h2d"]; rest_ms += ms["split"] + ms["hash"] + ms["format"] + ms["d2h"]
@@ -115,7 +133,7 @@ def main():
                 lo = int(members[k][3]); hi = int(members[last][0] + members[last][1]) + 8
                 stages[si][:hi - lo] = mv[lo:hi]
                 tab = members[k:last + 1, :3].copy(); tab[:, 0] -= np.uint64(lo)
-                r = t.run_bgzf(hi - lo, tab, n_own, extra, 0 if k == 0 else -1, last == n - 1, 1, ids, B.FLAG_UPPER, True, b"c5.fa")
+                r = t.run_bgzf(hi - lo, tab, n_own, extra, 0 if k == 0 else -1, last == n - 1, fmt, ids, B.FLAG_UPPER, True, b"c5.fa")
                 recs[si] += r[2]
                 inf_ms[si] += t.last_inflate_ms()
         best_dt = None
